@@ -1,0 +1,171 @@
+/*
+ * soundscope_b200.h — C ABI of the B200-native analyzer hot path (libsoundscope_b200.so).
+ *
+ * The reference (bananaofhappiness/soundscope v1.9.0) has no FFI for this path: the boundary is
+ * the inherent-method surface of `analyzer::Analyzer` (reference src/analyzer.rs:47-183) plus the
+ * free function `get_mid_and_side_samples` (reference src/audio_player.rs:400-419).  Every entry
+ * point below names the reference item it replaces.  A Rust shim that keeps `analyzer.rs`'s
+ * signatures and forwards to these symbols is given in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns an int32 status (SSB_OK == 0);
+ *   - a handle owns n_streams independent meters ("streams"); n_streams == 1 is exactly one
+ *     reference `Analyzer`.  Batched inputs are stream-major:  in[s][frame][channel] (each
+ *     stream's slice is what the reference would pass to `add_samples`);
+ *   - `*_device` variants take DEVICE pointers and are asynchronous on the handle's stream;
+ *     host variants copy through pinned staging and are complete (results valid, caller's
+ *     buffer reusable) at return;
+ *   - a handle is not thread-safe (the reference's `&mut self`); distinct handles may be used
+ *     concurrently;
+ *   - there is no CPU fallback: if no sm_100-class device is usable, create fails with
+ *     SSB_ERR_NO_DEVICE / SSB_ERR_CUDA.
+ */
+#ifndef SOUNDSCOPE_B200_H
+#define SOUNDSCOPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------ */
+enum {
+  SSB_OK = 0,
+  /* ebur128::Error (returned by add_samples / get_*_lufs / get_true_peak, analyzer.rs:139-164) */
+  SSB_ERR_NOMEM = 1,                 /* Error::NoMem: channels 0 or >64, rate <16 or >2822400, ragged input */
+  SSB_ERR_INVALID_MODE = 2,          /* Error::InvalidMode */
+  SSB_ERR_INVALID_CHANNEL_INDEX = 3, /* Error::InvalidChannelIndex (get_true_peak on a mono meter) */
+  /* spectrum_analyzer::SpectrumAnalyzerError surfaced by get_fft (analyzer.rs:60-65) */
+  SSB_ERR_FFT_TOO_FEW_SAMPLES = 4,
+  SSB_ERR_FFT_NAN = 5,
+  SSB_ERR_FFT_INF = 6,
+  SSB_ERR_FFT_NOT_POW2 = 7,          /* not a power of two, or above the crate's largest size (32768) */
+  SSB_ERR_FFT_BAD_LIMIT = 8,         /* 20 kHz upper limit above Nyquist */
+  SSB_ERR_FFT_SCALING = 9,
+  /* this library's own */
+  SSB_ERR_INVALID_ARG = 10,
+  SSB_ERR_CAPACITY = 11,             /* caller's output buffer too small; required size written to *n_out */
+  SSB_ERR_UNALIGNED_QUERY = 12,      /* momentary/short-term query off the 100 ms grid on a handle built without SSB_FLAG_RING */
+  SSB_ERR_NO_DEVICE = 13,
+  SSB_ERR_CUDA = 100                 /* 100 + cudaError_t */
+};
+
+/* ---- ebur128::Mode bits (the reference always passes Mode::all(), analyzer.rs:36,51,171) --- */
+enum {
+  SSB_MODE_M = 1 << 0,
+  SSB_MODE_S = (1 << 1) | SSB_MODE_M,
+  SSB_MODE_I = (1 << 2) | SSB_MODE_M,
+  SSB_MODE_LRA = (1 << 3) | SSB_MODE_S,
+  SSB_MODE_SAMPLE_PEAK = (1 << 4) | SSB_MODE_M,
+  SSB_MODE_TRUE_PEAK = (1 << 5) | SSB_MODE_M | SSB_MODE_SAMPLE_PEAK,
+  SSB_MODE_HISTOGRAM = 1 << 6,
+  SSB_MODE_ALL = 0x7f
+};
+
+/* ---- create flags ------------------------------------------------------------------------ */
+enum {
+  /* keep the 3 s ring of K-weighted samples per stream (what ebur128 keeps), so momentary and
+   * short-term queries are exact at ANY feed position, as the reference's tick loop needs
+   * (tui.rs:1528-1543 feeds 8192 frames per tick).  Costs 8 B/sample of extra HBM writes and
+   * 24*rate*channels bytes per stream; meant for few-stream, reference-shaped use.  Without it
+   * the handle keeps only per-100 ms energy sums (O(1) state per stream, the batch mode) and
+   * M/S queries are exact on the 100 ms grid and refused off it. */
+  SSB_FLAG_RING = 1 << 0
+};
+
+typedef struct ssb_analyzer ssb_analyzer;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+/* Analyzer::default() (analyzer.rs:34-45) == ssb_analyzer_create(&h, 2, 44100, SSB_MODE_ALL, 1, dev, SSB_FLAG_RING).
+ * `device` < 0 selects the current CUDA device. */
+int32_t ssb_analyzer_create(ssb_analyzer** out, uint32_t channels, uint32_t rate, int32_t mode,
+                            size_t n_streams, int32_t device, uint32_t flags);
+void ssb_analyzer_destroy(ssb_analyzer* h);
+/* Analyzer::create_loudness_meter (analyzer.rs:49-53): replace the meter(s), keep n_streams/flags/mode. */
+int32_t ssb_create_loudness_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate);
+/* Analyzer::sample_rate (analyzer.rs:166-168) */
+uint32_t ssb_sample_rate(const ssb_analyzer* h);
+uint32_t ssb_channels(const ssb_analyzer* h);
+size_t ssb_n_streams(const ssb_analyzer* h);
+/* last error text of this handle (never NULL) */
+const char* ssb_last_error(const ssb_analyzer* h);
+/* run this handle's work on a caller-owned CUDA stream (cudaStream_t); NULL restores the handle's own */
+int32_t ssb_set_stream(ssb_analyzer* h, void* cuda_stream);
+int32_t ssb_sync(ssb_analyzer* h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+uint64_t ssb_launch_count(const ssb_analyzer* h);
+
+/* ---- loudness: Analyzer::add_samples / reset / get_* (analyzer.rs:139-164) ---------------- */
+/* add_samples(&[f32]) -> EbuR128::add_frames_f32.  `interleaved` holds n_streams slices of
+ * frames_per_stream*channels f32 (HOST memory, pageable or pinned). */
+int32_t ssb_add_frames_f32(ssb_analyzer* h, const float* interleaved, size_t frames_per_stream);
+/* same, `interleaved` is a DEVICE pointer; asynchronous on the handle's stream */
+int32_t ssb_add_frames_f32_device(ssb_analyzer* h, const float* d_interleaved, size_t frames_per_stream);
+/* the reference's slice-length form: len = number of f32 for ONE stream; len % channels != 0 -> SSB_ERR_NOMEM */
+int32_t ssb_add_samples(ssb_analyzer* h, const float* interleaved, size_t len);
+int32_t ssb_reset(ssb_analyzer* h);
+/* out[n_streams]; -inf (not an error) where the reference returns -inf */
+int32_t ssb_loudness_momentary(ssb_analyzer* h, double* out);
+int32_t ssb_loudness_shortterm(ssb_analyzer* h, double* out); /* get_shortterm_lufs, analyzer.rs:147 */
+int32_t ssb_loudness_global(ssb_analyzer* h, double* out);    /* get_integrated_lufs, analyzer.rs:151 */
+int32_t ssb_loudness_range(ssb_analyzer* h, double* out);     /* get_loudness_range,  analyzer.rs:155 */
+/* out[n_streams*channels], linear amplitude = max(true peak, sample peak) as EbuR128::true_peak */
+int32_t ssb_true_peak(ssb_analyzer* h, double* out);
+int32_t ssb_sample_peak(ssb_analyzer* h, double* out);
+/* get_true_peak (analyzer.rs:159-164): channels 0 and 1 of stream 0; mono -> SSB_ERR_INVALID_CHANNEL_INDEX */
+int32_t ssb_get_true_peak(ssb_analyzer* h, double* left, double* right);
+/* all scalars in one pass, written to DEVICE memory as rows of ssb_result_stride(h) doubles:
+ * [momentary, shortterm, global, range, true_peak[channels], sample_peak[channels]] — the buffer
+ * the multi-GPU gather moves.  Asynchronous. */
+size_t ssb_result_stride(const ssb_analyzer* h);
+int32_t ssb_results_device(ssb_analyzer* h, double* d_out);
+/* Analyzer::calculate_integrated_lufs (analyzer.rs:170-182): fresh Mode::all() meter at the handle's
+ * rate, fed in chunks of sample_rate*2 samples.  *is_some = 0 mirrors `None`. */
+int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const float* samples,
+                                      size_t len, double* out, int32_t* is_some);
+
+/* ---- spectrum: Analyzer::get_fft (analyzer.rs:55-105) -------------------------------------- */
+/* one mono window of n samples (HOST) -> (x, dB) pairs, x = log-frequency position 0..100.
+ * xy_out holds cap pairs (2*cap doubles); *n_points = pairs produced (or required on SSB_ERR_CAPACITY). */
+int32_t ssb_get_fft(ssb_analyzer* h, const float* samples, size_t n, double* xy_out, size_t cap,
+                    size_t* n_points);
+/* number of bins get_fft keeps for (n, rate) and the first kept bin index */
+int32_t ssb_fft_bins(size_t n, uint32_t rate, size_t* k_first, size_t* n_bins);
+/* the (n, rate)-only part of get_fft's output: x[k] and the pink tilt 10*log10(f/1000) per kept bin */
+int32_t ssb_fft_axis(size_t n, uint32_t rate, double* x_out, double* tilt_out, size_t cap, size_t* n_bins);
+enum { SSB_FFT_MONO = 0, SSB_FFT_MID_SIDE = 1 };
+/* batched: n_windows windows of n frames (DEVICE).  SSB_FFT_MONO: in[w][n] f32.  SSB_FFT_MID_SIDE:
+ * in[w][n][2] interleaved stereo; mid/side are formed as get_mid_and_side_samples does
+ * (audio_player.rs:400-419) and both spectra are produced.  d_db_out[w][planes][n_bins] f32 receives
+ * scale_to_dbfs (analyzer.rs:11-27) BEFORE the f64 tilt (planes = 1 or 2); add ssb_fft_axis's tilt to
+ * get the reference's y.  d_status[w] (optional) receives per-window SSB_ERR_FFT_* codes. */
+int32_t ssb_fft_batch_device(ssb_analyzer* h, const float* d_in, int32_t layout, size_t n,
+                             size_t n_windows, float* d_db_out, int32_t* d_status);
+
+/* ---- waveform + mid/side (stateless) ------------------------------------------------------ */
+/* Analyzer::get_waveform (analyzer.rs:107-137): HOST samples -> (i, min), (i, max) pairs. */
+int32_t ssb_get_waveform(ssb_analyzer* h, const float* samples, size_t len, double waveform_window,
+                         double* xy_out, size_t cap, size_t* n_points);
+/* device form: d_minmax_out[2*columns] f32 (min, max per column); *n_columns = columns produced */
+int32_t ssb_waveform_device(ssb_analyzer* h, const float* d_samples, size_t len, double waveform_window,
+                            float* d_minmax_out, size_t cap_columns, size_t* n_columns);
+/* get_mid_and_side_samples (audio_player.rs:400-419): HOST in, HOST out; *frames = len/2 */
+int32_t ssb_mid_side(ssb_analyzer* h, const float* interleaved, size_t len, float* mid, float* side,
+                     size_t* frames);
+int32_t ssb_mid_side_device(ssb_analyzer* h, const float* d_interleaved, size_t len, float* d_mid,
+                            float* d_side);
+
+/* ---- introspection used by the tests ------------------------------------------------------ */
+int32_t ssb_filter_coeffs(const ssb_analyzer* h, double b[5], double a[5]);
+/* copy the two 1000-bin histograms of stream s to HOST */
+int32_t ssb_histograms(ssb_analyzer* h, size_t stream, uint64_t block[1000], uint64_t shortterm[1000]);
+uint32_t ssb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOUNDSCOPE_B200_H */

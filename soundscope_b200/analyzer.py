@@ -1,0 +1,143 @@
+"""Host-side mirror of the reference's `analyzer::Analyzer` (reference src/analyzer.rs:29-183).
+
+Same method names, argument meaning and error behaviour; every method is one call through the C ABI
+(include/soundscope_b200.h) into the CUDA kernels.  Inputs and outputs are host numpy arrays, as the
+reference's are host slices / Vecs.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import FLAG_RING, MODE_ALL, SsbError, check, lib
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data
+
+
+class Analyzer:
+    """One reference `Analyzer`: a Mode::all() loudness meter plus the stateless spectrum/waveform ops."""
+
+    def __init__(self, device=-1):
+        # Default (analyzer.rs:34-45): EbuR128::new(2, 44100, Mode::all()); panics on failure
+        self._h = C.c_void_p()
+        self._device = device
+        rc = lib().ssb_analyzer_create(C.byref(self._h), 2, 44100, MODE_ALL, 1, device, FLAG_RING)
+        if rc:
+            raise SsbError(rc, "Failed to create loudness meter")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ssb_analyzer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # analyzer.rs:49-53
+    def create_loudness_meter(self, channels, rate):
+        check(self._h, lib().ssb_create_loudness_meter(self._h, channels, rate))
+
+    # analyzer.rs:55-105 -> ndarray [n_points, 2] of (chart_x, dB)
+    def get_fft(self, samples):
+        a, p = _f32(samples)
+        cap = a.size // 2 + 1
+        out = np.empty((max(cap, 1), 2), dtype=np.float64)
+        n = C.c_size_t(0)
+        check(self._h, lib().ssb_get_fft(self._h, p, a.size, out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value]
+
+    # analyzer.rs:107-137 (associated fn in the reference; needs a device here, so any instance serves)
+    def get_waveform(self, samples, waveform_window):
+        a, p = _f32(samples)
+        n = C.c_size_t(0)
+        rc = lib().ssb_get_waveform(self._h, p, a.size, float(waveform_window), None, 0, C.byref(n))
+        if rc not in (0, 11):  # 11 = SSB_ERR_CAPACITY: the sizing call
+            check(self._h, rc)
+        out = np.empty((max(n.value, 1), 2), dtype=np.float64)
+        check(self._h, lib().ssb_get_waveform(self._h, p, a.size, float(waveform_window), out.ctypes.data,
+                                               n.value, C.byref(n)))
+        return out[: n.value]
+
+    # analyzer.rs:139-141
+    def add_samples(self, samples):
+        a, p = _f32(samples)
+        check(self._h, lib().ssb_add_samples(self._h, p, a.size))
+
+    # analyzer.rs:143-145
+    def reset(self):
+        check(self._h, lib().ssb_reset(self._h))
+
+    def _scalar(self, fn):
+        v = C.c_double(0)
+        check(self._h, fn(self._h, C.addressof(v)))
+        return v.value
+
+    def get_momentary_lufs(self):
+        return self._scalar(lib().ssb_loudness_momentary)
+
+    # analyzer.rs:147-149
+    def get_shortterm_lufs(self):
+        return self._scalar(lib().ssb_loudness_shortterm)
+
+    # analyzer.rs:151-153
+    def get_integrated_lufs(self):
+        return self._scalar(lib().ssb_loudness_global)
+
+    # analyzer.rs:155-157
+    def get_loudness_range(self):
+        return self._scalar(lib().ssb_loudness_range)
+
+    # analyzer.rs:159-164
+    def get_true_peak(self):
+        l, r = C.c_double(0), C.c_double(0)
+        check(self._h, lib().ssb_get_true_peak(self._h, C.byref(l), C.byref(r)))
+        return l.value, r.value
+
+    # analyzer.rs:166-168
+    def sample_rate(self):
+        return lib().ssb_sample_rate(self._h)
+
+    # analyzer.rs:170-182 -> float or None
+    def calculate_integrated_lufs(self, channels, samples):
+        a, p = _f32(samples)
+        out, some = C.c_double(0), C.c_int32(0)
+        check(self._h, lib().ssb_calculate_integrated_lufs(self._h, channels, p, a.size, C.byref(out), C.byref(some)))
+        return out.value if some.value else None
+
+    # introspection (tests)
+    def filter_coeffs(self):
+        b, a = np.zeros(5), np.zeros(5)
+        check(self._h, lib().ssb_filter_coeffs(self._h, b.ctypes.data, a.ctypes.data))
+        return b, a
+
+    def histograms(self, stream=0):
+        blk, st = np.zeros(1000, dtype=np.uint64), np.zeros(1000, dtype=np.uint64)
+        check(self._h, lib().ssb_histograms(self._h, stream, blk.ctypes.data, st.ctypes.data))
+        return blk, st
+
+    def get_mid_and_side_samples(self, samples):
+        return get_mid_and_side_samples(samples, self)
+
+
+_default = None
+
+
+def get_mid_and_side_samples(samples, analyzer=None):
+    """reference src/audio_player.rs:400-419 — (mid, side) f32 arrays of len(samples)//2 frames."""
+    global _default
+    if analyzer is None:
+        if _default is None:
+            _default = Analyzer()
+        analyzer = _default
+    a, p = _f32(samples)
+    frames = a.size // 2
+    mid = np.empty(frames, dtype=np.float32)
+    side = np.empty(frames, dtype=np.float32)
+    n = C.c_size_t(0)
+    check(analyzer._h, lib().ssb_mid_side(analyzer._h, p, a.size, mid.ctypes.data, side.ctypes.data, C.byref(n)))
+    return mid, side

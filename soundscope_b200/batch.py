@@ -1,0 +1,146 @@
+"""Batched, device-resident form of the analyzer path: n_streams independent meters per handle and
+batched spectra, driven with torch CUDA tensors (torch is plumbing: device memory, streams, NCCL).
+
+Layouts follow the C ABI (include/soundscope_b200.h): loudness input [n_streams, frames, channels] f32;
+FFT input [n_windows, n] (mono) or [n_windows, n, 2] (stereo -> mid/side).
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import FFT_MID_SIDE, FFT_MONO, MODE_ALL, SsbError, check, lib
+
+
+class BatchAnalyzer:
+    def __init__(self, n_streams, channels=2, rate=48000, mode=MODE_ALL, device=-1, flags=0, use_torch_stream=True):
+        self._h = C.c_void_p()
+        rc = lib().ssb_analyzer_create(C.byref(self._h), channels, rate, mode, n_streams, device, flags)
+        if rc:
+            raise SsbError(rc, "ssb_analyzer_create")
+        self.n_streams, self.channels, self.rate, self.mode = n_streams, channels, rate, mode
+        self.stride = lib().ssb_result_stride(self._h)
+        if use_torch_stream:
+            import torch
+            check(self._h, lib().ssb_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ssb_analyzer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return lib().ssb_launch_count(self._h)
+
+    def sync(self):
+        check(self._h, lib().ssb_sync(self._h))
+
+    def reset(self):
+        check(self._h, lib().ssb_reset(self._h))
+
+    def add_frames_device(self, x):
+        """x: torch.float32 CUDA tensor [n_streams, frames, channels], contiguous."""
+        assert x.is_cuda and x.is_contiguous() and x.dtype.is_floating_point and x.element_size() == 4
+        assert x.shape[0] == self.n_streams and x.shape[2] == self.channels
+        check(self._h, lib().ssb_add_frames_f32_device(self._h, C.c_void_p(x.data_ptr()), x.shape[1]))
+
+    def add_frames_host(self, x):
+        """x: host float32 array / pinned tensor [n_streams, frames, channels]; H2D copy is inside the call."""
+        if hasattr(x, "data_ptr"):
+            assert x.is_contiguous() and not x.is_cuda
+            ptr, frames = x.data_ptr(), x.shape[1]
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            ptr, frames = x.ctypes.data, x.shape[1]
+        check(self._h, lib().ssb_add_frames_f32(self._h, C.c_void_p(ptr), frames))
+
+    def results_device(self, out=None):
+        """[n_streams, 4+2C] f64 CUDA tensor: momentary, shortterm, integrated, LRA, true_peak[C], sample_peak[C]."""
+        import torch
+        if out is None:
+            out = torch.empty((self.n_streams, self.stride), dtype=torch.float64, device="cuda")
+        check(self._h, lib().ssb_results_device(self._h, C.c_void_p(out.data_ptr())))
+        return out
+
+    def _col(self, fn, width=1):
+        out = np.empty(self.n_streams * width, dtype=np.float64)
+        check(self._h, fn(self._h, out.ctypes.data))
+        return out if width == 1 else out.reshape(self.n_streams, width)
+
+    def loudness_momentary(self):
+        return self._col(lib().ssb_loudness_momentary)
+
+    def loudness_shortterm(self):
+        return self._col(lib().ssb_loudness_shortterm)
+
+    def loudness_global(self):
+        return self._col(lib().ssb_loudness_global)
+
+    def loudness_range(self):
+        return self._col(lib().ssb_loudness_range)
+
+    def true_peak(self):
+        return self._col(lib().ssb_true_peak, self.channels)
+
+    def sample_peak(self):
+        return self._col(lib().ssb_sample_peak, self.channels)
+
+    def histograms(self, stream):
+        blk, st = np.zeros(1000, dtype=np.uint64), np.zeros(1000, dtype=np.uint64)
+        check(self._h, lib().ssb_histograms(self._h, stream, blk.ctypes.data, st.ctypes.data))
+        return blk, st
+
+    # ---- spectrum -------------------------------------------------------------------------------
+    def fft_bins(self, n):
+        k0, nb = C.c_size_t(0), C.c_size_t(0)
+        check(self._h, lib().ssb_fft_bins(n, self.rate, C.byref(k0), C.byref(nb)))
+        return k0.value, nb.value
+
+    def fft_axis(self, n):
+        _, nb = self.fft_bins(n)
+        x, tilt = np.empty(nb), np.empty(nb)
+        m = C.c_size_t(0)
+        check(self._h, lib().ssb_fft_axis(n, self.rate, x.ctypes.data, tilt.ctypes.data, nb, C.byref(m)))
+        return x, tilt
+
+    def fft_batch_device(self, x, out=None, status=None):
+        """x: [W, n] (mono) or [W, n, 2] (stereo -> mid, side) f32 CUDA tensor -> dB [W, planes, n_bins] f32."""
+        import torch
+        assert x.is_cuda and x.is_contiguous()
+        layout = FFT_MID_SIDE if x.dim() == 3 else FFT_MONO
+        w, n = x.shape[0], x.shape[1]
+        _, nb = self.fft_bins(n)
+        planes = 2 if layout == FFT_MID_SIDE else 1
+        if out is None:
+            out = torch.empty((w, planes, nb), dtype=torch.float32, device=x.device)
+        sp = C.c_void_p(status.data_ptr()) if status is not None else None
+        check(self._h, lib().ssb_fft_batch_device(self._h, C.c_void_p(x.data_ptr()), layout, n, w,
+                                                  C.c_void_p(out.data_ptr()), sp))
+        return out
+
+    def waveform_device(self, x, waveform_window):
+        """x: 1-D f32 CUDA tensor -> [columns, 2] (min, max) f32 CUDA tensor."""
+        import torch
+        assert x.is_cuda and x.is_contiguous()
+        n = C.c_size_t(0)
+        lib().ssb_waveform_device(self._h, None, x.numel(), float(waveform_window), None, 0, C.byref(n))
+        out = torch.empty((n.value, 2), dtype=torch.float32, device=x.device)
+        check(self._h, lib().ssb_waveform_device(self._h, C.c_void_p(x.data_ptr()), x.numel(), float(waveform_window),
+                                                 C.c_void_p(out.data_ptr()), n.value, C.byref(n)))
+        return out
+
+    def mid_side_device(self, x):
+        import torch
+        assert x.is_cuda and x.is_contiguous()
+        frames = x.numel() // 2
+        mid = torch.empty(frames, dtype=torch.float32, device=x.device)
+        side = torch.empty(frames, dtype=torch.float32, device=x.device)
+        check(self._h, lib().ssb_mid_side_device(self._h, C.c_void_p(x.data_ptr()), x.numel(),
+                                                 C.c_void_p(mid.data_ptr()), C.c_void_p(side.data_ptr())))
+        return mid, side

@@ -1,0 +1,743 @@
+// capi.cu — the C ABI declared in include/soundscope_b200.h: handle, argument checks in the
+// reference's error vocabulary, staging, launch scheduling.  No compute happens on the host:
+// every entry point either launches the CUDA kernels or fails.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <memory>
+#include <new>
+
+#include "ssb_internal.cuh"
+
+using namespace ssb;
+
+struct ssb_analyzer {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  uint32_t channels = 0, rate = 0;
+  int32_t mode = 0;
+  size_t n_streams = 0;
+  uint32_t flags = 0;
+
+  LoudParams lp{};
+  GateParams gp{};
+  LoudState st{};
+  uint64_t total_frames = 0;  // frames fed per stream since the last reset
+  size_t ring_pos = 0;
+
+  double* d_hist_tables = nullptr;  // energies[1000] | boundaries[1001]
+  double* d_results = nullptr;
+  double* h_results = nullptr;  // pinned
+  bool results_valid = false;
+
+  float* d_stage[2] = {nullptr, nullptr};
+  size_t stage_cap = 0;  // floats per staging buffer
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  int stage_idx = 0;
+  float* d_scratch = nullptr;  // outputs of single-shot host calls
+  size_t scratch_cap = 0;      // bytes
+  void* h_scratch = nullptr;   // pinned mirror
+  size_t h_scratch_cap = 0;
+
+  std::map<std::pair<size_t, uint32_t>, FftPlan> plans;
+  std::map<std::pair<size_t, uint32_t>, std::pair<std::vector<double>, std::vector<double>>> axes;
+
+  uint64_t launches = 0;
+  char err[256] = {0};
+};
+
+namespace {
+
+int32_t fail(ssb_analyzer* h, int32_t code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+int32_t cuda_fail(ssb_analyzer* h, cudaError_t e, const char* what) {
+  return fail(h, SSB_ERR_CUDA + (int32_t)e, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CK(call)                                                  \
+  do {                                                            \
+    cudaError_t e__ = (call);                                     \
+    if (e__ != cudaSuccess) return cuda_fail(h, e__, #call);      \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+void free_meter(ssb_analyzer* h) {
+  cudaFree(h->st.filt); cudaFree(h->st.bucket); cudaFree(h->st.block_hist); cudaFree(h->st.st_hist);
+  cudaFree(h->st.speak); cudaFree(h->st.tpeak); cudaFree(h->st.tphist); cudaFree(h->st.ring);
+  cudaFree(h->d_results);
+  if (h->h_results) cudaFreeHost(h->h_results);
+  h->st = LoudState{};
+  h->d_results = nullptr;
+  h->h_results = nullptr;
+}
+
+// (re)build everything that depends on (channels, rate): EbuR128::new
+int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
+  if (channels == 0 || channels > (uint32_t)kMaxChannels)
+    return fail(h, SSB_ERR_NOMEM, "EbuR128::new: channels %u outside 1..=64 (Error::NoMem)", channels);
+  if (rate < 16 || rate > 2822400)
+    return fail(h, SSB_ERR_NOMEM, "EbuR128::new: rate %u outside 16..=2822400 (Error::NoMem)", rate);
+  free_meter(h);
+  h->channels = channels;
+  h->rate = rate;
+  LoudParams& lp = h->lp;
+  memset(&lp, 0, sizeof(lp));
+  kweight_coeffs(rate, lp.b, lp.a);
+  lp.channels = (int)channels;
+  lp.s100 = (rate + 5) / 10;
+  lp.do_filter = 1;  // every mode contains M
+  lp.do_sample_peak = (h->mode & SSB_MODE_SAMPLE_PEAK) == SSB_MODE_SAMPLE_PEAK;
+  lp.do_true_peak = (h->mode & SSB_MODE_TRUE_PEAK) == SSB_MODE_TRUE_PEAK;
+  lp.tp_factor = lp.do_true_peak ? truepeak_taps(rate, lp.tp4, lp.tp2) : 0;
+  GateParams& gp = h->gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.channels = (int)channels;
+  gp.s100 = lp.s100;
+  gp.do_i = (h->mode & SSB_MODE_I) == SSB_MODE_I;
+  gp.do_lra = (h->mode & SSB_MODE_LRA) == SSB_MODE_LRA;
+  default_channel_weights(channels, gp.weight, &lp.active_mask);
+
+  const size_t n = h->n_streams, chains = n * channels;
+  LoudState& st = h->st;
+  st.n_streams = n;
+  CK(cudaMalloc(&st.filt, chains * 4 * sizeof(double)));
+  CK(cudaMalloc(&st.bucket, chains * kNB * sizeof(double)));
+  CK(cudaMalloc(&st.block_hist, n * kHistBins * sizeof(uint32_t)));
+  CK(cudaMalloc(&st.st_hist, n * kHistBins * sizeof(uint32_t)));
+  CK(cudaMalloc(&st.speak, chains * sizeof(float)));
+  CK(cudaMalloc(&st.tpeak, chains * sizeof(float)));
+  CK(cudaMalloc(&st.tphist, chains * kTpHist * sizeof(float)));
+  st.ring = nullptr;
+  st.ring_frames = 0;
+  if (h->flags & SSB_FLAG_RING) {
+    // ebur128: 3 s (mode S) or 400 ms of filtered samples, rounded up to a multiple of samples_in_100ms
+    const size_t window_ms = ((h->mode & SSB_MODE_S) == SSB_MODE_S) ? 3000 : 400;
+    size_t rf = (size_t)rate * window_ms / 1000;
+    if (rf % lp.s100) rf = rf + lp.s100 - (rf % lp.s100);
+    st.ring_frames = rf;
+    CK(cudaMalloc(&st.ring, n * rf * channels * sizeof(double)));
+  }
+  st.hist_energies = h->d_hist_tables;
+  st.hist_boundaries = h->d_hist_tables + 1000;
+  const size_t stride = 4 + 2 * (size_t)channels;
+  CK(cudaMalloc(&h->d_results, n * stride * sizeof(double)));
+  CK(cudaMallocHost(&h->h_results, n * stride * sizeof(double)));
+  h->total_frames = 0;
+  h->ring_pos = 0;
+  h->results_valid = false;
+  CK(launch_reset(st, (int)channels, h->stream, &h->launches));
+  return SSB_OK;
+}
+
+int32_t ensure_stage(ssb_analyzer* h, size_t floats) {
+  if (floats <= h->stage_cap) return SSB_OK;
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 2; i++) {
+    cudaFree(h->d_stage[i]);
+    h->d_stage[i] = nullptr;
+    CK(cudaMalloc(&h->d_stage[i], floats * sizeof(float)));
+  }
+  h->stage_cap = floats;
+  return SSB_OK;
+}
+
+int32_t ensure_scratch(ssb_analyzer* h, size_t bytes) {
+  if (bytes > h->scratch_cap) {
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_scratch);
+    h->d_scratch = nullptr;
+    CK(cudaMalloc(&h->d_scratch, bytes));
+    h->scratch_cap = bytes;
+  }
+  if (bytes > h->h_scratch_cap) {
+    if (h->h_scratch) cudaFreeHost(h->h_scratch);
+    h->h_scratch = nullptr;
+    CK(cudaMallocHost(&h->h_scratch, bytes));
+    h->h_scratch_cap = bytes;
+  }
+  return SSB_OK;
+}
+
+// feed `frames` frames per stream from device memory laid out [stream][in_stride_frames][C]
+int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in_stride_frames) {
+  const uint32_t s100 = h->lp.s100;
+  const size_t C = h->channels;
+  size_t done = 0;
+  while (done < frames) {
+    const uint32_t pos = (uint32_t)(h->total_frames % s100);
+    const uint64_t bucket0 = h->total_frames / s100;
+    const size_t max_frames = (size_t)kMaxBucketsPerLaunch * s100 - pos;
+    const size_t n = frames - done < max_frames ? frames - done : max_frames;
+    CK(launch_loudness_generic(h->lp, h->st, d_in + done * C, n, in_stride_frames, pos, bucket0, h->ring_pos,
+                               h->stream, &h->launches));
+    const uint64_t completed = (pos + n) / s100;
+    if (completed) CK(launch_gating(h->gp, h->st, bucket0, bucket0 + completed - 1, h->stream, &h->launches));
+    h->total_frames += n;
+    if (h->st.ring_frames) h->ring_pos = (h->ring_pos + n) % h->st.ring_frames;
+    done += n;
+  }
+  h->results_valid = false;
+  return SSB_OK;
+}
+
+int32_t refresh_results(ssb_analyzer* h) {
+  if (h->results_valid) return SSB_OK;
+  const int aligned = (h->total_frames % h->lp.s100) == 0;
+  CK(launch_results(h->gp, h->st, h->total_frames / h->lp.s100, aligned, h->ring_pos, h->mode, h->d_results,
+                    h->stream, &h->launches));
+  const size_t stride = 4 + 2 * (size_t)h->channels;
+  CK(cudaMemcpyAsync(h->h_results, h->d_results, h->n_streams * stride * sizeof(double), cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->results_valid = true;
+  return SSB_OK;
+}
+
+int32_t get_plan(ssb_analyzer* h, size_t n, uint32_t rate, FftPlan** out) {
+  auto key = std::make_pair(n, rate);
+  auto it = h->plans.find(key);
+  if (it == h->plans.end()) {
+    FftPlan p;
+    p.n = n;
+    p.rate = rate;
+    p.n_bins = fft_bin_range(n, rate, &p.k_first);
+    std::vector<float> w;
+    hann_multipliers(n, w);
+    std::vector<float2> tw(n / 2 ? n / 2 : 1);
+    for (size_t k = 0; k < n / 2; k++) {
+      // exp(-j*2*pi*k/n), exact on the axes, rounded once from double elsewhere
+      if (k == 0) tw[k] = make_float2(1.f, 0.f);
+      else if (4 * k == n) tw[k] = make_float2(0.f, -1.f);
+      else {
+        const double ang = 2.0 * M_PI * (double)k / (double)n;
+        tw[k] = make_float2((float)cos(ang), (float)-sin(ang));
+      }
+    }
+    CK(cudaMalloc(&p.d_window, n * sizeof(float)));
+    CK(cudaMalloc(&p.d_twiddle, tw.size() * sizeof(float2)));
+    CK(cudaMemcpyAsync(p.d_window, w.data(), n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(p.d_twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));  // w / tw are locals
+    it = h->plans.emplace(key, p).first;
+  }
+  *out = &it->second;
+  return SSB_OK;
+}
+
+// spectrum-analyzer's argument checks that do not need the data
+int32_t fft_shape_check(size_t n, uint32_t rate) {
+  if (n < 2) return SSB_ERR_FFT_TOO_FEW_SAMPLES;
+  if ((n & (n - 1)) || n > 32768) return SSB_ERR_FFT_NOT_POW2;
+  if (20000.0f > (float)rate / 2.0f) return SSB_ERR_FFT_BAD_LIMIT;
+  return SSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t ssb_abi_version(void) { return SSB_ABI_VERSION; }
+
+int32_t ssb_analyzer_create(ssb_analyzer** out, uint32_t channels, uint32_t rate, int32_t mode, size_t n_streams,
+                            int32_t device, uint32_t flags) {
+  if (!out) return SSB_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (n_streams == 0) return SSB_ERR_INVALID_ARG;
+  if ((mode & SSB_MODE_M) == 0 || (mode & ~SSB_MODE_ALL)) return SSB_ERR_INVALID_MODE;
+  // integrated loudness / LRA are implemented in ebur128's histogram mode, the one Mode::all() selects
+  if (((mode & SSB_MODE_I) == SSB_MODE_I || (mode & SSB_MODE_LRA) == SSB_MODE_LRA) && !(mode & SSB_MODE_HISTOGRAM))
+    return SSB_ERR_INVALID_MODE;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return SSB_ERR_NO_DEVICE;
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) return SSB_ERR_NO_DEVICE;
+  }
+  if (device >= count) return SSB_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SSB_ERR_NO_DEVICE;
+  if (prop.major != 10) return SSB_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+  ssb_analyzer* h = new (std::nothrow) ssb_analyzer();
+  if (!h) return SSB_ERR_NOMEM;
+  h->device = device;
+  h->mode = mode;
+  h->n_streams = n_streams;
+  h->flags = flags;
+  DeviceGuard g(device);
+  int32_t rc = SSB_OK;
+  do {
+    if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking))) { rc = SSB_ERR_CUDA + e; break; }
+    h->stream = h->own_stream;
+    for (int i = 0; i < 2; i++) {
+      if ((e = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming))) { rc = SSB_ERR_CUDA + e; break; }
+      if ((e = cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming))) { rc = SSB_ERR_CUDA + e; break; }
+    }
+    if (rc) break;
+    double tables[2001];
+    histogram_tables(tables, tables + 1000);
+    if ((e = cudaMalloc(&h->d_hist_tables, sizeof(tables)))) { rc = SSB_ERR_CUDA + e; break; }
+    if ((e = cudaMemcpy(h->d_hist_tables, tables, sizeof(tables), cudaMemcpyHostToDevice))) { rc = SSB_ERR_CUDA + e; break; }
+    rc = init_meter(h, channels, rate);
+  } while (0);
+  if (rc != SSB_OK) {
+    ssb_analyzer_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return SSB_OK;
+}
+
+void ssb_analyzer_destroy(ssb_analyzer* h) {
+  if (!h) return;
+  DeviceGuard g(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_meter(h);
+  cudaFree(h->d_hist_tables);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(h->d_stage[i]);
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+  }
+  cudaFree(h->d_scratch);
+  if (h->h_scratch) cudaFreeHost(h->h_scratch);
+  for (auto& kv : h->plans) {
+    cudaFree(kv.second.d_window);
+    cudaFree(kv.second.d_twiddle);
+  }
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int32_t ssb_create_loudness_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
+  if (!h) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  // the reference stores the rate before EbuR128::new can fail (analyzer.rs:50-51)
+  const uint32_t old_rate = h->rate;
+  cudaStreamSynchronize(h->stream);
+  int32_t rc = init_meter(h, channels, rate);
+  if (rc == SSB_ERR_NOMEM) { h->rate = rate; (void)old_rate; }
+  return rc;
+}
+
+uint32_t ssb_sample_rate(const ssb_analyzer* h) { return h ? h->rate : 0; }
+uint32_t ssb_channels(const ssb_analyzer* h) { return h ? h->channels : 0; }
+size_t ssb_n_streams(const ssb_analyzer* h) { return h ? h->n_streams : 0; }
+const char* ssb_last_error(const ssb_analyzer* h) { return h ? h->err : "null handle"; }
+uint64_t ssb_launch_count(const ssb_analyzer* h) { return h ? h->launches : 0; }
+
+int32_t ssb_set_stream(ssb_analyzer* h, void* cuda_stream) {
+  if (!h) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return SSB_OK;
+}
+
+int32_t ssb_sync(ssb_analyzer* h) {
+  if (!h) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  return SSB_OK;
+}
+
+int32_t ssb_add_frames_f32_device(ssb_analyzer* h, const float* d_interleaved, size_t frames_per_stream) {
+  if (!h) return SSB_ERR_INVALID_ARG;
+  if (frames_per_stream == 0) return SSB_OK;
+  if (!d_interleaved) return fail(h, SSB_ERR_INVALID_ARG, "null input");
+  DeviceGuard g(h->device);
+  return feed_device(h, d_interleaved, frames_per_stream, frames_per_stream);
+}
+
+int32_t ssb_add_frames_f32(ssb_analyzer* h, const float* interleaved, size_t frames_per_stream) {
+  if (!h) return SSB_ERR_INVALID_ARG;
+  if (frames_per_stream == 0) return SSB_OK;
+  if (!interleaved) return fail(h, SSB_ERR_INVALID_ARG, "null input");
+  DeviceGuard g(h->device);
+  const size_t floats = h->n_streams * frames_per_stream * h->channels;
+  int32_t rc = ensure_stage(h, floats);
+  if (rc) return rc;
+  const int i = h->stage_idx;
+  h->stage_idx ^= 1;
+  // the staging buffer may still be read by the kernels of two calls ago
+  CK(cudaEventSynchronize(h->ev_consumed[i]));
+  CK(cudaMemcpyAsync(h->d_stage[i], interleaved, floats * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->ev_copied[i], h->stream));
+  rc = feed_device(h, h->d_stage[i], frames_per_stream, frames_per_stream);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev_consumed[i], h->stream));
+  CK(cudaEventSynchronize(h->ev_copied[i]));  // caller may reuse its buffer; kernels keep running
+  return SSB_OK;
+}
+
+int32_t ssb_add_samples(ssb_analyzer* h, const float* interleaved, size_t len) {
+  if (!h) return SSB_ERR_INVALID_ARG;
+  if (len % h->channels != 0)
+    return fail(h, SSB_ERR_NOMEM, "add_frames_f32: %zu samples is not a multiple of %u channels (Error::NoMem)", len,
+                h->channels);
+  return ssb_add_frames_f32(h, interleaved, len / h->channels);
+}
+
+int32_t ssb_reset(ssb_analyzer* h) {
+  if (!h) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  CK(launch_reset(h->st, (int)h->channels, h->stream, &h->launches));
+  h->total_frames = 0;
+  h->ring_pos = 0;
+  h->results_valid = false;
+  return SSB_OK;
+}
+
+static int32_t copy_column(ssb_analyzer* h, int col, double* out) {
+  const size_t stride = 4 + 2 * (size_t)h->channels;
+  for (size_t s = 0; s < h->n_streams; s++) out[s] = h->h_results[s * stride + col];
+  return SSB_OK;
+}
+
+int32_t ssb_loudness_momentary(ssb_analyzer* h, double* out) {
+  if (!h || !out) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  if (!h->st.ring && (h->total_frames % h->lp.s100) != 0)
+    return fail(h, SSB_ERR_UNALIGNED_QUERY, "momentary query %llu frames into a 100 ms block needs SSB_FLAG_RING",
+                (unsigned long long)(h->total_frames % h->lp.s100));
+  int32_t rc = refresh_results(h);
+  return rc ? rc : copy_column(h, 0, out);
+}
+
+int32_t ssb_loudness_shortterm(ssb_analyzer* h, double* out) {
+  if (!h || !out) return SSB_ERR_INVALID_ARG;
+  if ((h->mode & SSB_MODE_S) != SSB_MODE_S) return fail(h, SSB_ERR_INVALID_MODE, "mode lacks S (Error::InvalidMode)");
+  DeviceGuard g(h->device);
+  if (!h->st.ring && (h->total_frames % h->lp.s100) != 0)
+    return fail(h, SSB_ERR_UNALIGNED_QUERY, "short-term query %llu frames into a 100 ms block needs SSB_FLAG_RING",
+                (unsigned long long)(h->total_frames % h->lp.s100));
+  int32_t rc = refresh_results(h);
+  return rc ? rc : copy_column(h, 1, out);
+}
+
+int32_t ssb_loudness_global(ssb_analyzer* h, double* out) {
+  if (!h || !out) return SSB_ERR_INVALID_ARG;
+  if ((h->mode & SSB_MODE_I) != SSB_MODE_I) return fail(h, SSB_ERR_INVALID_MODE, "mode lacks I (Error::InvalidMode)");
+  DeviceGuard g(h->device);
+  int32_t rc = refresh_results(h);
+  return rc ? rc : copy_column(h, 2, out);
+}
+
+int32_t ssb_loudness_range(ssb_analyzer* h, double* out) {
+  if (!h || !out) return SSB_ERR_INVALID_ARG;
+  if ((h->mode & SSB_MODE_LRA) != SSB_MODE_LRA) return fail(h, SSB_ERR_INVALID_MODE, "mode lacks LRA (Error::InvalidMode)");
+  DeviceGuard g(h->device);
+  int32_t rc = refresh_results(h);
+  return rc ? rc : copy_column(h, 3, out);
+}
+
+int32_t ssb_true_peak(ssb_analyzer* h, double* out) {
+  if (!h || !out) return SSB_ERR_INVALID_ARG;
+  if ((h->mode & SSB_MODE_TRUE_PEAK) != SSB_MODE_TRUE_PEAK)
+    return fail(h, SSB_ERR_INVALID_MODE, "mode lacks TRUE_PEAK (Error::InvalidMode)");
+  DeviceGuard g(h->device);
+  int32_t rc = refresh_results(h);
+  if (rc) return rc;
+  const size_t C = h->channels, stride = 4 + 2 * C;
+  for (size_t s = 0; s < h->n_streams; s++)
+    for (size_t c = 0; c < C; c++) out[s * C + c] = h->h_results[s * stride + 4 + c];
+  return SSB_OK;
+}
+
+int32_t ssb_sample_peak(ssb_analyzer* h, double* out) {
+  if (!h || !out) return SSB_ERR_INVALID_ARG;
+  if ((h->mode & SSB_MODE_SAMPLE_PEAK) != SSB_MODE_SAMPLE_PEAK)
+    return fail(h, SSB_ERR_INVALID_MODE, "mode lacks SAMPLE_PEAK (Error::InvalidMode)");
+  DeviceGuard g(h->device);
+  int32_t rc = refresh_results(h);
+  if (rc) return rc;
+  const size_t C = h->channels, stride = 4 + 2 * C;
+  for (size_t s = 0; s < h->n_streams; s++)
+    for (size_t c = 0; c < C; c++) out[s * C + c] = h->h_results[s * stride + 4 + C + c];
+  return SSB_OK;
+}
+
+int32_t ssb_get_true_peak(ssb_analyzer* h, double* left, double* right) {
+  if (!h || !left || !right) return SSB_ERR_INVALID_ARG;
+  if ((h->mode & SSB_MODE_TRUE_PEAK) != SSB_MODE_TRUE_PEAK)
+    return fail(h, SSB_ERR_INVALID_MODE, "mode lacks TRUE_PEAK (Error::InvalidMode)");
+  if (h->channels < 2) return fail(h, SSB_ERR_INVALID_CHANNEL_INDEX, "true_peak(1) on a mono meter (Error::InvalidChannelIndex)");
+  DeviceGuard g(h->device);
+  int32_t rc = refresh_results(h);
+  if (rc) return rc;
+  *left = h->h_results[4];
+  *right = h->h_results[5];
+  return SSB_OK;
+}
+
+size_t ssb_result_stride(const ssb_analyzer* h) { return h ? 4 + 2 * (size_t)h->channels : 0; }
+
+int32_t ssb_results_device(ssb_analyzer* h, double* d_out) {
+  if (!h || !d_out) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  const int aligned = (h->total_frames % h->lp.s100) == 0;
+  CK(launch_results(h->gp, h->st, h->total_frames / h->lp.s100, aligned, h->ring_pos, h->mode, d_out, h->stream,
+                    &h->launches));
+  return SSB_OK;
+}
+
+int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const float* samples, size_t len,
+                                      double* out, int32_t* is_some) {
+  if (!h || !out || !is_some || (!samples && len)) return SSB_ERR_INVALID_ARG;
+  *is_some = 0;
+  DeviceGuard g(h->device);
+  ssb_analyzer* tmp = nullptr;
+  int32_t rc = ssb_analyzer_create(&tmp, channels, h->rate, SSB_MODE_ALL, 1, h->device, 0);
+  if (rc == SSB_ERR_NOMEM) return SSB_OK;  // EbuR128::new failed -> None
+  if (rc) return fail(h, rc, "calculate_integrated_lufs: cannot create meter");
+  // analyzer.rs:175: chunks(sample_rate * 2); a chunk that is not whole frames makes add_frames_f32 fail -> None
+  const size_t chunk = (size_t)h->rate * 2;
+  bool ok = true;
+  for (size_t off = 0; off < len && ok; off += chunk) {
+    const size_t n = len - off < chunk ? len - off : chunk;
+    if (n % channels != 0) ok = false;
+  }
+  if (ok && len) {
+    float* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, len * sizeof(float));
+    if (e) { ssb_analyzer_destroy(tmp); return cuda_fail(h, e, "cudaMalloc"); }
+    e = cudaMemcpyAsync(d, samples, len * sizeof(float), cudaMemcpyHostToDevice, tmp->stream);
+    for (size_t off = 0; off < len && !e && !rc; off += chunk) {
+      const size_t n = len - off < chunk ? len - off : chunk;
+      rc = feed_device(tmp, d + off, n / channels, n / channels);
+    }
+    if (!e && !rc) e = cudaStreamSynchronize(tmp->stream);
+    cudaFree(d);
+    if (e) { ssb_analyzer_destroy(tmp); return cuda_fail(h, e, "calculate_integrated_lufs"); }
+  }
+  if (!rc && ok) {
+    double v = 0;
+    rc = ssb_loudness_global(tmp, &v);
+    if (!rc) { *out = v; *is_some = 1; }
+  }
+  h->launches += tmp->launches;
+  ssb_analyzer_destroy(tmp);
+  return rc;
+}
+
+int32_t ssb_fft_bins(size_t n, uint32_t rate, size_t* k_first, size_t* n_bins) {
+  if (!n_bins) return SSB_ERR_INVALID_ARG;
+  int32_t rc = fft_shape_check(n, rate);
+  if (rc) return rc;
+  size_t k0 = 0;
+  *n_bins = fft_bin_range(n, rate, &k0);
+  if (k_first) *k_first = k0;
+  return SSB_OK;
+}
+
+int32_t ssb_fft_axis(size_t n, uint32_t rate, double* x_out, double* tilt_out, size_t cap, size_t* n_bins) {
+  if (!n_bins) return SSB_ERR_INVALID_ARG;
+  int32_t rc = fft_shape_check(n, rate);
+  if (rc) return rc;
+  std::vector<double> x, t;
+  fft_axis(n, rate, x, t, nullptr);
+  *n_bins = x.size();
+  if (x.size() > cap) return SSB_ERR_CAPACITY;
+  if (x_out) memcpy(x_out, x.data(), x.size() * sizeof(double));
+  if (tilt_out) memcpy(tilt_out, t.data(), t.size() * sizeof(double));
+  return SSB_OK;
+}
+
+int32_t ssb_fft_batch_device(ssb_analyzer* h, const float* d_in, int32_t layout, size_t n, size_t n_windows,
+                             float* d_db_out, int32_t* d_status) {
+  if (!h || !d_in || !d_db_out) return SSB_ERR_INVALID_ARG;
+  if (layout != SSB_FFT_MONO && layout != SSB_FFT_MID_SIDE) return fail(h, SSB_ERR_INVALID_ARG, "bad layout");
+  int32_t rc = fft_shape_check(n, h->rate);
+  if (rc) return fail(h, rc, "get_fft: invalid length %zu / rate %u", n, h->rate);
+  DeviceGuard g(h->device);
+  FftPlan* plan = nullptr;
+  rc = get_plan(h, n, h->rate, &plan);
+  if (rc) return rc;
+  CK(launch_fft(*plan, d_in, layout, n_windows, d_db_out, d_status, h->stream, &h->launches));
+  return SSB_OK;
+}
+
+int32_t ssb_get_fft(ssb_analyzer* h, const float* samples, size_t n, double* xy_out, size_t cap, size_t* n_points) {
+  if (!h || !n_points || (!samples && n)) return SSB_ERR_INVALID_ARG;
+  *n_points = 0;
+  int32_t shape = fft_shape_check(n, h->rate);
+  if (shape == SSB_ERR_FFT_TOO_FEW_SAMPLES) return fail(h, shape, "get_fft: too few samples (%zu)", n);
+  if (shape) {
+    // the crate checks NaN / infinity of the WINDOWED samples before the length and the limit; the Hann
+    // multiplier is finite and only multiplier[0] is zero (0 * inf = NaN), so inspect the input directly
+    bool any_nan = false, any_inf = false;
+    for (size_t i = 0; i < n; i++) {
+      if (isnan(samples[i]) || (i == 0 && isinf(samples[i]))) any_nan = true;
+      else if (isinf(samples[i])) any_inf = true;
+    }
+    if (any_nan) return fail(h, SSB_ERR_FFT_NAN, "get_fft: NaN values not supported");
+    if (any_inf) return fail(h, SSB_ERR_FFT_INF, "get_fft: infinity values not supported");
+    return fail(h, shape, shape == SSB_ERR_FFT_NOT_POW2 ? "get_fft: length %zu is not a supported power of two"
+                                                          : "get_fft: 20 kHz limit above Nyquist (n=%zu)", n);
+  }
+  DeviceGuard g(h->device);
+  FftPlan* plan = nullptr;
+  int32_t rc = get_plan(h, n, h->rate, &plan);
+  if (rc) return rc;
+  const size_t nb = plan->n_bins;
+  *n_points = nb;
+  if (nb > cap || !xy_out) return fail(h, SSB_ERR_CAPACITY, "get_fft: need room for %zu points", nb);
+  const size_t in_bytes = n * sizeof(float), out_bytes = nb * sizeof(float) + sizeof(int32_t);
+  const size_t out_off = (in_bytes + 255) & ~(size_t)255;
+  rc = ensure_scratch(h, out_off + out_bytes + 256);
+  if (rc) return rc;
+  float* d_in = h->d_scratch;
+  float* d_db = reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_scratch) + out_off);
+  int32_t* d_status = reinterpret_cast<int32_t*>(d_db + nb);
+  CK(cudaMemcpyAsync(d_in, samples, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(launch_fft(*plan, d_in, SSB_FFT_MONO, 1, d_db, d_status, h->stream, &h->launches));
+  CK(cudaMemcpyAsync(h->h_scratch, d_db, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const float* db = static_cast<const float*>(h->h_scratch);
+  const int32_t status = *reinterpret_cast<const int32_t*>(db + nb);
+  if (status) return fail(h, status, "get_fft: window rejected (%d)", status);
+  auto key = std::make_pair(n, h->rate);
+  auto it = h->axes.find(key);
+  if (it == h->axes.end()) {
+    std::vector<double> x, t;
+    fft_axis(n, h->rate, x, t, nullptr);
+    it = h->axes.emplace(key, std::make_pair(std::move(x), std::move(t))).first;
+  }
+  const std::vector<double>& ax = it->second.first;
+  const std::vector<double>& tilt = it->second.second;
+  for (size_t i = 0; i < nb; i++) {
+    xy_out[2 * i] = ax[i];
+    xy_out[2 * i + 1] = (double)db[i] + tilt[i];  // analyzer.rs:82-84: val as f64 + compensation
+  }
+  return SSB_OK;
+}
+
+static size_t waveform_window_columns(double waveform_window, size_t len, size_t* window_out) {
+  const double w = waveform_window * 1000.;
+  size_t window = 0;  // Rust `as usize` saturates; NaN -> 0
+  if (w > 0.0) window = w >= 18446744073709551615.0 ? SIZE_MAX : (size_t)w;
+  *window_out = window;
+  if (!window || !len) return 0;
+  const double spp = (double)len / (double)window;
+  // the loop breaks at the first column whose start is past the end (analyzer.rs:122-124); starts are monotone
+  size_t cols = window;
+  while (cols > 0 && (size_t)((double)(cols - 1) * spp) >= len) cols--;
+  return cols;
+}
+
+int32_t ssb_waveform_device(ssb_analyzer* h, const float* d_samples, size_t len, double waveform_window,
+                            float* d_minmax_out, size_t cap_columns, size_t* n_columns) {
+  if (!h || !n_columns) return SSB_ERR_INVALID_ARG;
+  size_t window = 0;
+  const size_t cols = waveform_window_columns(waveform_window, len, &window);
+  *n_columns = cols;
+  if (cols > cap_columns) return fail(h, SSB_ERR_CAPACITY, "get_waveform: need room for %zu columns", cols);
+  if (!cols) return SSB_OK;
+  if (!d_samples || !d_minmax_out) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  CK(launch_waveform(d_samples, len, window, d_minmax_out, cols, h->stream, &h->launches));
+  return SSB_OK;
+}
+
+int32_t ssb_get_waveform(ssb_analyzer* h, const float* samples, size_t len, double waveform_window, double* xy_out,
+                         size_t cap, size_t* n_points) {
+  if (!h || !n_points || (!samples && len)) return SSB_ERR_INVALID_ARG;
+  size_t window = 0;
+  const size_t cols = waveform_window_columns(waveform_window, len, &window);
+  *n_points = 2 * cols;
+  if (2 * cols > cap || (cols && !xy_out)) return fail(h, SSB_ERR_CAPACITY, "get_waveform: need room for %zu points", 2 * cols);
+  if (!cols) return SSB_OK;
+  DeviceGuard g(h->device);
+  const size_t in_bytes = len * sizeof(float), out_bytes = cols * 2 * sizeof(float);
+  const size_t out_off = (in_bytes + 255) & ~(size_t)255;
+  int32_t rc = ensure_scratch(h, out_off + out_bytes);
+  if (rc) return rc;
+  float* d_in = h->d_scratch;
+  float* d_out = reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_scratch) + out_off);
+  CK(cudaMemcpyAsync(d_in, samples, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(launch_waveform(d_in, len, window, d_out, cols, h->stream, &h->launches));
+  CK(cudaMemcpyAsync(h->h_scratch, d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const float* mm = static_cast<const float*>(h->h_scratch);
+  for (size_t i = 0; i < cols; i++) {
+    xy_out[4 * i + 0] = (double)i;
+    xy_out[4 * i + 1] = (double)mm[2 * i];
+    xy_out[4 * i + 2] = (double)i;
+    xy_out[4 * i + 3] = (double)mm[2 * i + 1];
+  }
+  return SSB_OK;
+}
+
+int32_t ssb_mid_side_device(ssb_analyzer* h, const float* d_interleaved, size_t len, float* d_mid, float* d_side) {
+  if (!h) return SSB_ERR_INVALID_ARG;
+  const size_t frames = len / 2;
+  if (!frames) return SSB_OK;
+  if (!d_interleaved || !d_mid || !d_side) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  CK(launch_mid_side(d_interleaved, frames, d_mid, d_side, h->stream, &h->launches));
+  return SSB_OK;
+}
+
+int32_t ssb_mid_side(ssb_analyzer* h, const float* interleaved, size_t len, float* mid, float* side, size_t* frames_out) {
+  if (!h || !frames_out || (!interleaved && len)) return SSB_ERR_INVALID_ARG;
+  const size_t frames = len / 2;  // zip(): an odd trailing sample is dropped
+  *frames_out = frames;
+  if (!frames) return SSB_OK;
+  if (!mid || !side) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  const size_t in_bytes = frames * 2 * sizeof(float), half = frames * sizeof(float);
+  const size_t out_off = (in_bytes + 255) & ~(size_t)255;
+  int32_t rc = ensure_scratch(h, out_off + 2 * half);
+  if (rc) return rc;
+  float* d_in = h->d_scratch;
+  float* d_mid = reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_scratch) + out_off);
+  float* d_side = d_mid + frames;
+  CK(cudaMemcpyAsync(d_in, interleaved, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(launch_mid_side(d_in, frames, d_mid, d_side, h->stream, &h->launches));
+  CK(cudaMemcpyAsync(mid, d_mid, half, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(side, d_side, half, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SSB_OK;
+}
+
+int32_t ssb_filter_coeffs(const ssb_analyzer* h, double b[5], double a[5]) {
+  if (!h || !b || !a) return SSB_ERR_INVALID_ARG;
+  memcpy(b, h->lp.b, sizeof(h->lp.b));
+  memcpy(a, h->lp.a, sizeof(h->lp.a));
+  return SSB_OK;
+}
+
+int32_t ssb_histograms(ssb_analyzer* h, size_t stream, uint64_t block[1000], uint64_t shortterm[1000]) {
+  if (!h || stream >= h->n_streams || !block || !shortterm) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  std::vector<uint32_t> tmp(2 * kHistBins);
+  CK(cudaMemcpyAsync(tmp.data(), h->st.block_hist + stream * kHistBins, kHistBins * sizeof(uint32_t),
+                     cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(tmp.data() + kHistBins, h->st.st_hist + stream * kHistBins, kHistBins * sizeof(uint32_t),
+                     cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < kHistBins; i++) { block[i] = tmp[i]; shortterm[i] = tmp[kHistBins + i]; }
+  return SSB_OK;
+}
+
+}  // extern "C"

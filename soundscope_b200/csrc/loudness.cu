@@ -1,0 +1,378 @@
+// loudness.cu — BS.1770 / EBU R128 meter kernels (generic path), gating and result kernels.
+//
+// Replaces, for n_streams independent meters, what `EbuR128::add_frames_f32` and the loudness
+// queries do for one (reference src/analyzer.rs:139-164; crate ebur128 0.1.10 = libebur128):
+//   k_loudness_generic  one thread per (stream, channel): sample peak, polyphase true peak (f32),
+//                       4th-order DF-II K-weighting in f64, y^2 accumulated into per-100 ms buckets,
+//                       optional ring of y (SSB_FLAG_RING)
+//   k_gating            per stream: 400 ms block energies -> block histogram; 3 s energies -> short-term histogram
+//   k_results           per stream (one warp): momentary, short-term, integrated (histogram gating), LRA, peaks
+//
+// State layout in HBM (all stream-major):
+//   filt[n][C][4] f64 | bucket[n][C][64] f64 | block_hist[n][1000] u32 | st_hist[n][1000] u32
+//   speak/tpeak[n][C] f32 | tphist[n][C][24] f32 | ring[n][ring_frames][C] f64 (optional)
+#include "ssb_internal.cuh"
+
+namespace ssb {
+
+// ------------------------------------------------------------------------------------------------
+// generic filter kernel: fully general in channels / rate / chunking; thread per (stream, channel)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_loudness_generic(const LoudParams p, const float* __restrict__ in, size_t frames, size_t in_stride_frames,
+                   size_t n_streams, double* __restrict__ filt, double* __restrict__ bucket,
+                   float* __restrict__ speak, float* __restrict__ tpeak, float* __restrict__ tphist,
+                   double* __restrict__ ring, size_t ring_frames, size_t ring_pos, uint32_t pos0,
+                   uint32_t slot0) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = p.channels;
+  if (idx >= n_streams * (size_t)C) return;
+  const size_t stream = idx / C;
+  const int c = (int)(idx % C);
+  const float* x_ptr = in + stream * in_stride_frames * C + c;
+  const bool active = p.do_filter && ((p.active_mask >> c) & 1ull);
+
+  double v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+  if (active) {
+    const double* f = filt + idx * 4;
+    v1 = f[0]; v2 = f[1]; v3 = f[2]; v4 = f[3];
+  }
+  double* bk = bucket + idx * kNB;
+  uint32_t slot = slot0, pos = pos0;
+  double acc = (active && pos0 > 0) ? bk[slot] : 0.0;
+
+  float h[kTpHist];  // h[t] = x[n-1-t]
+  float sp = 0.f, tp = 0.f;
+  const bool do_tp = p.do_true_peak && p.tp_factor != 0;
+  if (do_tp) {
+#pragma unroll
+    for (int t = 0; t < kTpHist; t++) h[t] = tphist[idx * kTpHist + t];
+  }
+  double* rg = ring ? ring + stream * ring_frames * C + c : nullptr;
+  size_t rpos = ring_pos;
+
+  for (size_t i = 0; i < frames; i++) {
+    const float xf = x_ptr[i * C];
+    if (p.do_sample_peak) sp = fmaxf(sp, fabsf(xf));
+    if (do_tp) {
+      if (p.tp_factor == 4) {
+#pragma unroll
+        for (int f = 0; f < 3; f++) {
+          float a = xf * p.tp4[f][0];
+#pragma unroll
+          for (int t = 1; t < 12; t++) a = fmaf(h[t - 1], p.tp4[f][t], a);
+          tp = fmaxf(tp, fabsf(a));
+        }
+      } else {
+        float a = xf * p.tp2[0];
+#pragma unroll
+        for (int t = 1; t < 24; t++) a = fmaf(h[t - 1], p.tp2[t], a);
+        tp = fmaxf(tp, fabsf(a));
+      }
+#pragma unroll
+      for (int t = kTpHist - 1; t > 0; t--) h[t] = h[t - 1];
+      h[0] = xf;
+    }
+    if (active) {
+      // v0 = x - a1 v1 - a2 v2 - a3 v3 - a4 v4, the newest state last to keep the dependent chain short
+      double t = fma(-p.a[4], v4, (double)xf);
+      t = fma(-p.a[3], v3, t);
+      t = fma(-p.a[2], v2, t);
+      const double v0 = fma(-p.a[1], v1, t);
+      double y = p.b[4] * v4;
+      y = fma(p.b[3], v3, y);
+      y = fma(p.b[2], v2, y);
+      y = fma(p.b[1], v1, y);
+      y = fma(p.b[0], v0, y);
+      v4 = v3; v3 = v2; v2 = v1; v1 = v0;
+      acc = fma(y, y, acc);
+      if (rg) {
+        rg[rpos * C] = y;
+        if (++rpos == ring_frames) rpos = 0;
+      }
+    } else if (rg) {
+      rg[rpos * C] = 0.0;
+      if (++rpos == ring_frames) rpos = 0;
+    }
+    if (++pos == p.s100) {
+      bk[slot] = acc;
+      acc = 0.0;
+      pos = 0;
+      slot = (slot + 1) % kNB;
+    }
+  }
+  bk[slot] = acc;  // running sum of the (possibly empty) bucket in progress
+  if (active) {
+    // libebur128 flushes denormal filter state at the end of every call
+    double* f = filt + idx * 4;
+    f[0] = fabs(v1) < 2.2250738585072014e-308 ? 0.0 : v1;
+    f[1] = fabs(v2) < 2.2250738585072014e-308 ? 0.0 : v2;
+    f[2] = fabs(v3) < 2.2250738585072014e-308 ? 0.0 : v3;
+    f[3] = fabs(v4) < 2.2250738585072014e-308 ? 0.0 : v4;
+  }
+  if (p.do_sample_peak) speak[idx] = fmaxf(speak[idx], sp);
+  if (do_tp) {
+    tpeak[idx] = fmaxf(tpeak[idx], tp);
+#pragma unroll
+    for (int t = 0; t < kTpHist; t++) tphist[idx * kTpHist + t] = h[t];
+  }
+}
+
+cudaError_t launch_loudness_generic(const LoudParams& p, const LoudState& st, const float* d_in,
+                                    size_t frames, size_t in_stride_frames, uint32_t pos0,
+                                    uint64_t bucket0, size_t ring_pos, cudaStream_t s, uint64_t* launches) {
+  const size_t chains = st.n_streams * (size_t)p.channels;
+  if (!chains || !frames) return cudaSuccess;
+  const int tpb = 128;
+  const unsigned blocks = (unsigned)((chains + tpb - 1) / tpb);
+  k_loudness_generic<<<blocks, tpb, 0, s>>>(p, d_in, frames, in_stride_frames, st.n_streams, st.filt,
+                                            st.bucket, st.speak, st.tpeak, st.tphist, st.ring,
+                                            st.ring_frames, ring_pos, pos0, (uint32_t)(bucket0 % kNB));
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// gating: block / short-term energies of the buckets completed by the last filter launch
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_histogram_index(const double* __restrict__ bounds, double energy) {
+  int lo = 0, hi = 1000;
+  do {
+    const int mid = (lo + hi) >> 1;
+    if (energy >= bounds[mid]) lo = mid; else hi = mid;
+  } while (hi - lo != 1);
+  return lo;
+}
+
+// channel-weighted sum of `nb` buckets ending at bucket j (ebur128 calc_gating_block: per channel
+// sum, surround channels x1.41, summed over channels in channel order)
+__device__ __forceinline__ double window_energy(const double* __restrict__ bk, const GateParams& g, uint64_t j,
+                                                int nb) {
+  double sum = 0.0;
+  for (int c = 0; c < g.channels; c++) {
+    const float w = g.weight[c];
+    if (w == 0.0f) continue;
+    double ch = 0.0;
+    for (int k = nb - 1; k >= 0; k--) ch += bk[c * kNB + (int)((j - k) % kNB)];
+    if (w != 1.0f) ch *= 1.41;
+    sum += ch;
+  }
+  return sum / (double)((uint64_t)nb * g.s100);
+}
+
+__global__ void __launch_bounds__(128)
+k_gating(const GateParams g, size_t n_streams, const double* __restrict__ bucket,
+         uint32_t* __restrict__ block_hist, uint32_t* __restrict__ st_hist,
+         const double* __restrict__ bounds, uint64_t j_first, uint64_t j_last) {
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_streams) return;
+  const double* bk = bucket + s * (size_t)g.channels * kNB;
+  for (uint64_t j = j_first; j <= j_last; j++) {
+    if (g.do_i && j >= 3) {
+      const double e = window_energy(bk, g, j, 4);
+      if (e >= bounds[0]) block_hist[s * kHistBins + find_histogram_index(bounds, e)]++;
+    }
+    if (g.do_lra && j >= 29 && (j - 29) % 10 == 0) {
+      const double e = window_energy(bk, g, j, 30);
+      if (e >= bounds[0]) st_hist[s * kHistBins + find_histogram_index(bounds, e)]++;
+    }
+  }
+}
+
+cudaError_t launch_gating(const GateParams& g, const LoudState& st, uint64_t j_first, uint64_t j_last,
+                          cudaStream_t s, uint64_t* launches) {
+  if (!st.n_streams || j_last < j_first || !(g.do_i || g.do_lra)) return cudaSuccess;
+  const int tpb = 128;
+  k_gating<<<(unsigned)((st.n_streams + tpb - 1) / tpb), tpb, 0, s>>>(g, st.n_streams, st.bucket, st.block_hist,
+                                                                      st.st_hist, st.hist_boundaries, j_first, j_last);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// results: one warp per stream
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double energy_to_loudness(double e) { return 10.0 * log10(e) - 0.691; }
+
+// mean square of the last `win_frames` frames of the ring ending at ring_pos (ebur128 calc_gating_block
+// over the ring; the ring starts zeroed, so an under-filled window reads zeros exactly as the crate does)
+__device__ double ring_energy(const double* __restrict__ rg, const GateParams& g, size_t ring_frames,
+                              size_t ring_pos, size_t win_frames, int lane) {
+  double sum = 0.0;
+  for (int c = 0; c < g.channels; c++) {
+    const float w = g.weight[c];
+    if (w == 0.0f) continue;
+    double part = 0.0;
+    for (size_t i = lane; i < win_frames; i += 32) {
+      size_t idx = ring_pos + ring_frames - win_frames + i;
+      if (idx >= ring_frames) idx -= ring_frames;
+      const double y = rg[idx * g.channels + c];
+      part = fma(y, y, part);
+    }
+    double ch = warp_sum(part);
+    if (w != 1.0f) ch *= 1.41;
+    sum += ch;
+  }
+  return sum / (double)win_frames;
+}
+
+__global__ void __launch_bounds__(128)
+k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucket,
+          const uint32_t* __restrict__ block_hist, const uint32_t* __restrict__ st_hist,
+          const float* __restrict__ speak, const float* __restrict__ tpeak, const double* __restrict__ ring,
+          size_t ring_frames, size_t ring_pos, const double* __restrict__ energies,
+          const double* __restrict__ bounds, uint64_t buckets_done, int aligned, int mode,
+          double* __restrict__ out) {
+  const size_t s = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= n_streams) return;
+  const int C = g.channels;
+  const size_t stride = 4 + 2 * (size_t)C;
+  double* o = out + s * stride;
+  const double NaN = __longlong_as_double(0x7ff8000000000000ll);
+  const double NEG_INF = __longlong_as_double(0xfff0000000000000ll);
+
+  // --- momentary / short-term ---
+  double e_m = NaN, e_s = NaN;
+  if (ring) {
+    const double* rg = ring + s * ring_frames * C;
+    e_m = ring_energy(rg, g, ring_frames, ring_pos, (size_t)g.s100 * 4, lane);
+    if ((mode & SSB_MODE_S) == SSB_MODE_S) e_s = ring_energy(rg, g, ring_frames, ring_pos, (size_t)g.s100 * 30, lane);
+  } else if (aligned) {
+    // buckets not yet produced since the last reset hold zeros, like the crate's zeroed ring
+    const double* bk = bucket + s * (size_t)C * kNB;
+    const uint64_t j = buckets_done + kNB - 1;  // last completed bucket, biased to stay non-negative mod kNB
+    e_m = window_energy(bk, g, j, 4);
+    if ((mode & SSB_MODE_S) == SSB_MODE_S) e_s = window_energy(bk, g, j, 30);
+  }
+  if (lane == 0) {
+    o[0] = (e_m == e_m) ? (e_m <= 0.0 ? NEG_INF : energy_to_loudness(e_m)) : NaN;
+    o[1] = (e_s == e_s) ? (e_s <= 0.0 ? NEG_INF : energy_to_loudness(e_s)) : NaN;
+  }
+
+  // --- integrated: ebur128 gated_loudness, histogram branch ---
+  double integrated = NaN;
+  if ((mode & SSB_MODE_I) == SSB_MODE_I) {
+    const uint32_t* hb = block_hist + s * kHistBins;
+    double pw = 0.0;
+    unsigned long long cnt = 0;
+    for (int i = lane; i < kHistBins; i += 32) {
+      const uint32_t hgt = hb[i];
+      pw = fma((double)hgt, energies[i], pw);
+      cnt += hgt;
+    }
+    pw = warp_sum(pw);
+    cnt = warp_sum_u64(cnt);
+    if (!cnt) integrated = NEG_INF;
+    else {
+      double rel = pw / (double)cnt;
+      rel *= 0.1;  // 10^(-10/10)
+      int start;
+      if (rel < bounds[0]) start = 0;
+      else {
+        start = find_histogram_index(bounds, rel);
+        if (rel > energies[start]) ++start;
+      }
+      double gp = 0.0;
+      unsigned long long gc = 0;
+      for (int i = lane; i < kHistBins; i += 32) {
+        if (i < start) continue;
+        const uint32_t hgt = hb[i];
+        gp = fma((double)hgt, energies[i], gp);
+        gc += hgt;
+      }
+      gp = warp_sum(gp);
+      gc = warp_sum_u64(gc);
+      integrated = gc ? energy_to_loudness(gp / (double)gc) : NEG_INF;
+    }
+  }
+  // --- loudness range: ebur128 loudness_range, histogram branch (EBU Tech 3342) ---
+  double lra = NaN;
+  if ((mode & SSB_MODE_LRA) == SSB_MODE_LRA) {
+    const uint32_t* hs = st_hist + s * kHistBins;
+    double pw = 0.0;
+    unsigned long long cnt = 0;
+    for (int i = lane; i < kHistBins; i += 32) {
+      const uint32_t hgt = hs[i];
+      pw = fma((double)hgt, energies[i], pw);
+      cnt += hgt;
+    }
+    pw = warp_sum(pw);
+    cnt = warp_sum_u64(cnt);
+    if (!cnt) lra = 0.0;
+    else {
+      const double stl_integrated = 0.01 * (pw / (double)cnt);  // 10^(-20/10)
+      int index;
+      if (stl_integrated < bounds[0]) index = 0;
+      else {
+        index = find_histogram_index(bounds, stl_integrated);
+        if (stl_integrated > energies[index]) ++index;
+      }
+      unsigned long long above = 0;
+      for (int i = lane; i < kHistBins; i += 32) if (i >= index) above += hs[i];
+      above = warp_sum_u64(above);
+      if (!above) lra = 0.0;
+      else if (lane == 0) {
+        const unsigned long long lo = (unsigned long long)((double)(above - 1) * 0.1 + 0.5);
+        const unsigned long long hi = (unsigned long long)((double)(above - 1) * 0.95 + 0.5);
+        unsigned long long run = 0;
+        int j = index;
+        while (run <= lo) run += hs[j++];
+        const double l_en = energies[j - 1];
+        while (run <= hi) run += hs[j++];
+        const double h_en = energies[j - 1];
+        lra = energy_to_loudness(h_en) - energy_to_loudness(l_en);
+      }
+    }
+  }
+  if (lane == 0) {
+    o[2] = integrated;
+    o[3] = lra;
+  }
+  // --- peaks: EbuR128::true_peak = max(true_peak, sample_peak) ---
+  for (int c = lane; c < C; c += 32) {
+    const float spv = speak[s * C + c], tpv = tpeak[s * C + c];
+    o[4 + c] = (double)fmaxf(spv, tpv);
+    o[4 + C + c] = (double)spv;
+  }
+}
+
+cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
+                           size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches) {
+  if (!st.n_streams) return cudaSuccess;
+  const int tpb = 128;
+  const size_t threads = st.n_streams * 32;
+  k_results<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, s>>>(
+      g, st.n_streams, st.bucket, st.block_hist, st.st_hist, st.speak, st.tpeak, st.ring, st.ring_frames,
+      ring_pos, st.hist_energies, st.hist_boundaries, buckets_done, aligned, mode, d_out);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reset(const LoudState& st, int channels, cudaStream_t s, uint64_t* launches) {
+  const size_t chains = st.n_streams * (size_t)channels;
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(st.filt, 0, chains * 4 * sizeof(double), s))) return e;
+  if ((e = cudaMemsetAsync(st.bucket, 0, chains * kNB * sizeof(double), s))) return e;
+  if ((e = cudaMemsetAsync(st.block_hist, 0, st.n_streams * kHistBins * sizeof(uint32_t), s))) return e;
+  if ((e = cudaMemsetAsync(st.st_hist, 0, st.n_streams * kHistBins * sizeof(uint32_t), s))) return e;
+  if ((e = cudaMemsetAsync(st.speak, 0, chains * sizeof(float), s))) return e;
+  if ((e = cudaMemsetAsync(st.tpeak, 0, chains * sizeof(float), s))) return e;
+  if ((e = cudaMemsetAsync(st.tphist, 0, chains * kTpHist * sizeof(float), s))) return e;
+  if (st.ring && (e = cudaMemsetAsync(st.ring, 0, st.n_streams * st.ring_frames * channels * sizeof(double), s))) return e;
+  (void)launches;
+  return cudaSuccess;
+}
+
+}  // namespace ssb

@@ -1,0 +1,297 @@
+// spectrum.cu — Analyzer::get_fft (reference src/analyzer.rs:55-105), get_waveform (:107-137) and
+// get_mid_and_side_samples (reference src/audio_player.rs:400-419) as CUDA kernels.
+//
+// k_fft<LAYOUT>: one CTA per window.  Load stage fuses de-interleave + mid/side (f32, exactly the
+// reference's (l+r)/2, (l-r)/2) + Hann multiply (host-built table of spectrum-analyzer's f32
+// multipliers); the transform is an in-place shared-memory radix-4 DIF (final radix-2 when log2 is odd)
+// whose digit-reversed result is read back only at the kept bins; the store stage fuses the real
+// split (two real spectra from one complex transform for mid/side; the packed N/2-point trick for
+// mono), |X| -> scale_to_dbfs (analyzer.rs:11-27) and the spectrum-analyzer argument checks.
+#include "ssb_internal.cuh"
+
+namespace ssb {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+  return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+}
+
+// W_N^k = exp(-j*2*pi*k/N) from the half table T[k], k < N/2
+__device__ __forceinline__ float2 tw_n(const float2* __restrict__ T, unsigned k, unsigned half_n) {
+  if (k < half_n) return __ldg(&T[k]);
+  const float2 t = __ldg(&T[k - half_n]);
+  return make_float2(-t.x, -t.y);
+}
+
+// position of X[k] after the in-place DIF with radices 4,4,...,(2): digit reversal
+__device__ __forceinline__ unsigned dif_position(unsigned k, unsigned M) {
+  unsigned p = 0, span = M;
+  while (span >= 4) { span >>= 2; p += (k & 3u) * span; k >>= 2; }
+  if (span == 2) p += (k & 1u);
+  return p;
+}
+
+__device__ void fft_inplace(float2* z, unsigned M, unsigned N, const float2* __restrict__ T) {
+  const unsigned tid = threadIdx.x, nt = blockDim.x;
+  unsigned L = M;
+  while (L >= 4) {
+    const unsigned Q = L >> 2;
+    const unsigned step = N / L;  // W_L^e = W_N^(e*step)
+    for (unsigned t = tid; t < (M >> 2); t += nt) {
+      const unsigned blk = t / Q, j = t - blk * Q;
+      const unsigned base = blk * L + j;
+      const float2 a0 = z[base], a1 = z[base + Q], a2 = z[base + 2 * Q], a3 = z[base + 3 * Q];
+      const float2 t0 = make_float2(a0.x + a2.x, a0.y + a2.y);
+      const float2 t1 = make_float2(a0.x - a2.x, a0.y - a2.y);
+      const float2 t2 = make_float2(a1.x + a3.x, a1.y + a3.y);
+      const float2 d = make_float2(a1.x - a3.x, a1.y - a3.y);
+      const float2 t3 = make_float2(d.y, -d.x);  // -j * (a1 - a3)
+      const float2 y0 = make_float2(t0.x + t2.x, t0.y + t2.y);
+      const float2 y1 = make_float2(t1.x + t3.x, t1.y + t3.y);
+      const float2 y2 = make_float2(t0.x - t2.x, t0.y - t2.y);
+      const float2 y3 = make_float2(t1.x - t3.x, t1.y - t3.y);
+      z[base] = y0;
+      if (j == 0) {
+        z[base + Q] = y1; z[base + 2 * Q] = y2; z[base + 3 * Q] = y3;
+      } else {
+        const unsigned e = j * step;
+        z[base + Q] = cmul(y1, tw_n(T, e, N >> 1));
+        z[base + 2 * Q] = cmul(y2, tw_n(T, 2 * e, N >> 1));
+        z[base + 3 * Q] = cmul(y3, tw_n(T, 3 * e, N >> 1));
+      }
+    }
+    __syncthreads();
+    L = Q;
+  }
+  if (L == 2) {
+    for (unsigned t = tid; t < (M >> 1); t += nt) {
+      const float2 a = z[2 * t], b = z[2 * t + 1];
+      z[2 * t] = make_float2(a.x + b.x, a.y + b.y);
+      z[2 * t + 1] = make_float2(a.x - b.x, a.y - b.y);
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ float mag_to_dbfs(float re, float im, float nf, int* bad) {
+  // spectrum-analyzer complex_to_magnitude (no fused multiply-add) then analyzer.rs:11-27
+  const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+  if (m == 0.0f) return -150.0f;
+  const float scaled = __fdiv_rn(__fmul_rn(m, 4.0f), nf);
+  const float db = 20.0f * log10f(scaled);
+  if (!isfinite(db)) *bad = 1;
+  return db;
+}
+
+// LAYOUT 0: mono, in[w][N].  LAYOUT 1: stereo in[w][N][2] -> mid & side planes.
+// LAYOUT 2 / 3: stereo input, only the mid / only the side plane through the packed-real path
+// (used when N complex points do not fit in shared memory).
+template <int LAYOUT>
+__global__ void __launch_bounds__(512)
+k_fft(const float* __restrict__ in, unsigned N, const float* __restrict__ window,
+      const float2* __restrict__ T, unsigned k_first, unsigned n_bins, float* __restrict__ db_out,
+      unsigned planes_out, unsigned plane_off, int32_t* __restrict__ status) {
+  extern __shared__ float2 z[];
+  __shared__ int s_flags[3];  // nan, inf, scaling
+  const unsigned w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const unsigned M = (LAYOUT == 1) ? N : (N >> 1);
+  if (tid < 3) s_flags[tid] = 0;
+  __syncthreads();
+  int f_nan = 0, f_inf = 0;
+  const float nf = (float)N;
+  if (LAYOUT == 1) {
+    const float2* src = reinterpret_cast<const float2*>(in) + (size_t)w * N;
+    for (unsigned n = tid; n < N; n += nt) {
+      const float2 lr = __ldg(&src[n]);
+      const float wn = __ldg(&window[n]);
+      const float mid = __fmul_rn(__fadd_rn(lr.x, lr.y), 0.5f);
+      const float side = __fmul_rn(__fsub_rn(lr.x, lr.y), 0.5f);
+      const float2 v = make_float2(__fmul_rn(wn, mid), __fmul_rn(wn, side));
+      f_nan |= (isnan(v.x) ? 1 : 0) | (isnan(v.y) ? 2 : 0);
+      f_inf |= (isinf(v.x) ? 1 : 0) | (isinf(v.y) ? 2 : 0);
+      z[n] = v;
+    }
+  } else {
+    for (unsigned m = tid; m < M; m += nt) {
+      float x0, x1;
+      if (LAYOUT == 0) {
+        const float2 p = __ldg(reinterpret_cast<const float2*>(in + (size_t)w * N) + m);
+        x0 = p.x; x1 = p.y;
+      } else {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(in + (size_t)w * N * 2) + m);
+        if (LAYOUT == 2) { x0 = __fmul_rn(__fadd_rn(p.x, p.y), 0.5f); x1 = __fmul_rn(__fadd_rn(p.z, p.w), 0.5f); }
+        else { x0 = __fmul_rn(__fsub_rn(p.x, p.y), 0.5f); x1 = __fmul_rn(__fsub_rn(p.z, p.w), 0.5f); }
+      }
+      const float2 wn = __ldg(reinterpret_cast<const float2*>(window) + m);
+      const float2 v = make_float2(__fmul_rn(wn.x, x0), __fmul_rn(wn.y, x1));
+      f_nan |= (isnan(v.x) || isnan(v.y)) ? 1 : 0;
+      f_inf |= (isinf(v.x) || isinf(v.y)) ? 1 : 0;
+      z[m] = v;
+    }
+  }
+  if (f_nan) atomicOr(&s_flags[0], f_nan);
+  if (f_inf) atomicOr(&s_flags[1], f_inf);
+  __syncthreads();
+  // twiddles of every stage are expressed as powers of W_N (W_L^e = W_N^(e*N/L)), so the one half table
+  // serves both the N-point (mid/side) and the packed N/2-point (mono) transforms
+  if (M > 1) fft_inplace(z, M, N, T);
+  int bad = 0;
+  if (LAYOUT == 1) {
+    float* o_mid = db_out + ((size_t)w * planes_out + 0) * n_bins;
+    float* o_side = db_out + ((size_t)w * planes_out + 1) * n_bins;
+    for (unsigned i = tid; i < n_bins; i += nt) {
+      const unsigned k = k_first + i;
+      const float2 a = z[dif_position(k, M)];
+      const float2 b = z[dif_position((N - k) & (N - 1), M)];
+      const float mr = 0.5f * (a.x + b.x), mi = 0.5f * (a.y - b.y);
+      const float sr = 0.5f * (a.y + b.y), si = -0.5f * (a.x - b.x);
+      o_mid[i] = mag_to_dbfs(mr, mi, nf, &bad);
+      o_side[i] = mag_to_dbfs(sr, si, nf, &bad);
+    }
+  } else {
+    float* o = db_out + ((size_t)w * planes_out + plane_off) * n_bins;
+    for (unsigned i = tid; i < n_bins; i += nt) {
+      const unsigned k = k_first + i;
+      float xr, xi;
+      if (k == M) {
+        const float2 z0 = z[0];
+        xr = z0.x - z0.y; xi = 0.0f;
+      } else {
+        const float2 a = z[dif_position(k, M)];
+        const float2 b = z[dif_position(M - k, M)];
+        const float sr = 0.5f * (a.x + b.x), si = 0.5f * (a.y - b.y);
+        const float dr = 0.5f * (a.x - b.x), di = 0.5f * (a.y + b.y);
+        const float2 wk = __ldg(&T[k]);  // W_N^k, k < N/2
+        xr = sr + (wk.x * di + wk.y * dr);
+        xi = si + (wk.y * di - wk.x * dr);
+      }
+      o[i] = mag_to_dbfs(xr, xi, nf, &bad);
+    }
+  }
+  if (bad) atomicOr(&s_flags[2], 1);
+  __syncthreads();
+  if (status && tid == 0) {
+    if (LAYOUT == 1) {
+      for (int pl = 0; pl < 2; pl++) {
+        int32_t st = SSB_OK;
+        if (s_flags[0] & (1 << pl)) st = SSB_ERR_FFT_NAN;
+        else if (s_flags[1] & (1 << pl)) st = SSB_ERR_FFT_INF;
+        else if (s_flags[2]) st = SSB_ERR_FFT_SCALING;
+        status[(size_t)w * planes_out + pl] = st;
+      }
+    } else {
+      int32_t st = SSB_OK;
+      if (s_flags[0]) st = SSB_ERR_FFT_NAN;
+      else if (s_flags[1]) st = SSB_ERR_FFT_INF;
+      else if (s_flags[2]) st = SSB_ERR_FFT_SCALING;
+      status[(size_t)w * planes_out + plane_off] = st;
+    }
+  }
+}
+
+template <int LAYOUT>
+static cudaError_t launch_fft_layout(const FftPlan& plan, const float* d_in, size_t n_windows, float* d_db,
+                                     unsigned planes_out, unsigned plane_off, int32_t* d_status, cudaStream_t s) {
+  const unsigned N = (unsigned)plan.n;
+  const unsigned M = (LAYOUT == 1) ? N : (N >> 1);
+  const size_t smem = (size_t)(M ? M : 1) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(k_fft<LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e) return e;
+  unsigned threads = M / 4 < 64 ? 64 : (M / 4 > 512 ? 512 : M / 4);
+  k_fft<LAYOUT><<<(unsigned)n_windows, threads, smem, s>>>(d_in, N, plan.d_window, plan.d_twiddle,
+                                                          (unsigned)plan.k_first, (unsigned)plan.n_bins, d_db,
+                                                          planes_out, plane_off, d_status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fft(const FftPlan& plan, const float* d_in, int layout, size_t n_windows, float* d_db_out,
+                       int32_t* d_status, cudaStream_t s, uint64_t* launches) {
+  if (!n_windows) return cudaSuccess;
+  cudaError_t e;
+  if (layout == SSB_FFT_MONO) {
+    e = launch_fft_layout<0>(plan, d_in, n_windows, d_db_out, 1, 0, d_status, s);
+    if (launches) ++*launches;
+    return e;
+  }
+  if (plan.n <= 16384) {
+    e = launch_fft_layout<1>(plan, d_in, n_windows, d_db_out, 2, 0, d_status, s);
+    if (launches) ++*launches;
+    return e;
+  }
+  e = launch_fft_layout<2>(plan, d_in, n_windows, d_db_out, 2, 0, d_status, s);
+  if (e) return e;
+  e = launch_fft_layout<3>(plan, d_in, n_windows, d_db_out, 2, 1, d_status, s);
+  if (launches) *launches += 2;
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// get_waveform: min/max decimation.  Column bounds are the reference's f64 expressions, evaluated
+// with IEEE mul/div/ceil on the device (bit-exact with analyzer.rs:118-120).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_waveform(const float* __restrict__ x, unsigned long long len, double spp, unsigned long long columns,
+           float* __restrict__ out) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long i = warp; i < columns; i += n_warps) {
+    const unsigned long long start = (unsigned long long)__dmul_rn((double)i, spp);
+    unsigned long long end = (unsigned long long)ceil(__dmul_rn((double)(i + 1), spp));
+    if (end > len) end = len;
+    float mn, mx;
+    if (end > start) {
+      mn = mx = x[start];  // Rust reduce(): first element seeds, NaN-ignoring f32::min / f32::max
+      for (unsigned long long j = start + lane; j < end; j += 32) {
+        const float v = x[j];
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+    } else {
+      mn = mx = 0.0f;
+    }
+    if (lane == 0) { out[2 * i] = mn; out[2 * i + 1] = mx; }
+  }
+}
+
+cudaError_t launch_waveform(const float* d_samples, size_t len, size_t window, float* d_minmax, size_t columns,
+                            cudaStream_t s, uint64_t* launches) {
+  if (!columns) return cudaSuccess;
+  const double spp = (double)len / (double)window;
+  const unsigned tpb = 256;
+  size_t warps = columns;
+  size_t blocks = (warps * 32 + tpb - 1) / tpb;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_waveform<<<(unsigned)blocks, tpb, 0, s>>>(d_samples, (unsigned long long)len, spp,
+                                              (unsigned long long)columns, d_minmax);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// get_mid_and_side_samples
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mid_side(const float2* __restrict__ in, size_t frames, float* __restrict__ mid, float* __restrict__ side) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < frames; i += (size_t)gridDim.x * blockDim.x) {
+    const float2 lr = __ldg(&in[i]);
+    mid[i] = __fmul_rn(__fadd_rn(lr.x, lr.y), 0.5f);
+    side[i] = __fmul_rn(__fsub_rn(lr.x, lr.y), 0.5f);
+  }
+}
+
+cudaError_t launch_mid_side(const float* d_in, size_t frames, float* d_mid, float* d_side, cudaStream_t s,
+                            uint64_t* launches) {
+  if (!frames) return cudaSuccess;
+  size_t blocks = (frames + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_mid_side<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float2*>(d_in), frames, d_mid, d_side);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace ssb

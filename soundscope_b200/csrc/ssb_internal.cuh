@@ -1,0 +1,96 @@
+// ssb_internal.cuh — shared declarations of libsoundscope_b200.so (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/soundscope_b200.h"
+
+namespace ssb {
+
+constexpr int kMaxChannels = 64;
+constexpr int kNB = 64;              // per-100 ms energy buckets kept per (stream, channel)
+constexpr int kMaxBucketsPerLaunch = kNB - 31;  // so a 3 s window ending at any bucket of the launch is intact
+constexpr int kHistBins = 1000;
+constexpr int kTpHist = 24;          // input samples of true-peak history kept per (stream, channel)
+
+// Parameters of the K-weighting + peak kernels; passed by value (lives in the constant bank).
+struct LoudParams {
+  double b[5];
+  double a[5];          // a[0] == 1, unused
+  float tp4[3][12];     // factor-4 interpolator, phases 1..3, tap t multiplies x[n-t]
+  float tp2[24];        // factor-2 interpolator, phase 1
+  int tp_factor;        // 0 (none), 2 or 4 — ebur128's rate rule
+  int channels;
+  uint32_t s100;        // samples_in_100ms
+  int do_filter, do_sample_peak, do_true_peak;
+  uint64_t active_mask; // bit c set: channel c is not Channel::Unused
+};
+
+struct GateParams {
+  int channels;
+  uint32_t s100;
+  int do_i, do_lra;
+  float weight[kMaxChannels];  // 1.0 / 1.41 / 0.0 (unused)
+};
+
+// --- host-side tables (host_tables.cu) ---------------------------------------------------------
+void kweight_coeffs(uint32_t rate, double b[5], double a[5]);
+void default_channel_weights(uint32_t channels, float w[kMaxChannels], uint64_t* active_mask);
+int truepeak_taps(uint32_t rate, float tp4[3][12], float tp2[24]);   // returns factor 0/2/4
+void histogram_tables(double energies[1000], double boundaries[1001]);
+float libm_cosf(float x);                                            // libm 0.2.16 (musl) cosf
+void hann_multipliers(size_t n, std::vector<float>& w);             // spectrum-analyzer hann_window
+size_t fft_bin_range(size_t n, uint32_t rate, size_t* k_first);
+void fft_axis(size_t n, uint32_t rate, std::vector<double>& x, std::vector<double>& tilt, size_t* k_first);
+
+// --- kernel launchers (loudness.cu) ------------------------------------------------------------
+struct LoudState {
+  size_t n_streams;
+  double* filt;       // [n][C][4]
+  double* bucket;     // [n][C][kNB]
+  uint32_t* block_hist;  // [n][1000]
+  uint32_t* st_hist;     // [n][1000]
+  float* speak;       // [n][C]
+  float* tpeak;       // [n][C]
+  float* tphist;      // [n][C][kTpHist]
+  double* ring;       // [n][ring_frames][C] or nullptr
+  size_t ring_frames;
+  const double* hist_energies;    // [1000]
+  const double* hist_boundaries;  // [1001]
+};
+
+// Filters `frames` frames per stream starting `pos0` frames into 100 ms bucket number `bucket0`.
+// At most kMaxBucketsPerLaunch buckets may complete inside one call.
+cudaError_t launch_loudness_generic(const LoudParams& p, const LoudState& st, const float* d_in,
+                                    size_t frames, size_t in_stride_frames, uint32_t pos0,
+                                    uint64_t bucket0, size_t ring_pos, cudaStream_t s, uint64_t* launches);
+// Gating for buckets [j_first, j_last] completed by the preceding filter launch.
+cudaError_t launch_gating(const GateParams& g, const LoudState& st, uint64_t j_first, uint64_t j_last,
+                          cudaStream_t s, uint64_t* launches);
+// Per-stream scalars -> d_out[n][4+2C]; aligned != 0: the feed position is on the 100 ms grid.
+cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
+                           size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_reset(const LoudState& st, int channels, cudaStream_t s, uint64_t* launches);
+
+// --- kernel launchers (spectrum.cu) ------------------------------------------------------------
+struct FftPlan {
+  size_t n = 0;
+  uint32_t rate = 0;
+  size_t k_first = 0, n_bins = 0;
+  float* d_window = nullptr;   // [n] Hann multipliers
+  float2* d_twiddle = nullptr; // [n/2] exp(-j*2*pi*k/n)
+};
+cudaError_t launch_fft(const FftPlan& plan, const float* d_in, int layout, size_t n_windows,
+                       float* d_db_out, int32_t* d_status, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_waveform(const float* d_samples, size_t len, size_t window, float* d_minmax,
+                            size_t columns, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_mid_side(const float* d_in, size_t frames, float* d_mid, float* d_side,
+                            cudaStream_t s, uint64_t* launches);
+
+}  // namespace ssb

@@ -1,0 +1,79 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, and refuses to run without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "soundscope_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ssb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(ssb):
+    L = ctypes.CDLL(ssb.library_path())
+    names = header_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/soundscope_b200.h but not exported"
+    from soundscope_b200._lib import SYMBOLS
+    assert sorted(SYMBOLS) == names
+
+
+def test_abi_version(ssb):
+    assert ssb.lib().ssb_abi_version() == 1
+
+
+def test_no_cpu_fallback(ssb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(ssb.SsbError) as e:
+        ssb.Analyzer()
+    assert e.value.code == 13  # SSB_ERR_NO_DEVICE
+
+
+def test_product_does_not_reference_oracle():
+    pkg = os.path.join(ROOT, "soundscope_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+                if f.endswith((".cu", ".cuh", ".cpp")):
+                    assert '#include "oracle' not in src and "orc_" not in src, f
+
+
+def test_stateless_abi_calls(ssb):
+    L = ssb.lib()
+    k0, nb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    assert L.ssb_fft_bins(16384, 44100, ctypes.byref(k0), ctypes.byref(nb)) == 0
+    assert (k0.value, nb.value) == (8, 7423)
+    assert L.ssb_fft_bins(16384, 48000, ctypes.byref(k0), ctypes.byref(nb)) == 0
+    assert (k0.value, nb.value) == (7, 6820)
+    assert L.ssb_fft_bins(8192, 48000, ctypes.byref(k0), ctypes.byref(nb)) == 0
+    assert (k0.value, nb.value) == (4, 3410)
+    assert L.ssb_fft_bins(1000, 48000, ctypes.byref(k0), ctypes.byref(nb)) == 7   # not a power of two
+    assert L.ssb_fft_bins(65536, 48000, ctypes.byref(k0), ctypes.byref(nb)) == 7  # above the crate's largest size
+    assert L.ssb_fft_bins(1, 48000, ctypes.byref(k0), ctypes.byref(nb)) == 4
+    assert L.ssb_fft_bins(4096, 22050, ctypes.byref(k0), ctypes.byref(nb)) == 8   # 20 kHz above Nyquist
+    assert L.ssb_fft_bins(4096, 40000, ctypes.byref(k0), ctypes.byref(nb)) == 0   # 20000 <= 20000
+
+
+def test_fft_axis_matches_oracle(ssb, oracle):
+    import numpy as np
+    from tests.signals import ref_sine_f32
+    L = ssb.lib()
+    for n, rate in ((16384, 44100), (16384, 48000), (8192, 48000), (4096, 96000)):
+        k0, nb = oracle.fft_bin_range(n, rate)
+        x, t = np.empty(nb), np.empty(nb)
+        m = ctypes.c_size_t(0)
+        assert L.ssb_fft_axis(n, rate, x.ctypes.data, t.ctypes.data, nb, ctypes.byref(m)) == 0
+        assert m.value == nb
+        ref = oracle.get_fft(ref_sine_f32(1000.0, n, rate), rate)
+        assert np.array_equal(x, ref[:, 0])  # chart x depends only on (n, rate): bit-exact
