@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — the analyzer hot path on BASELINE.json's metric: audio samples/s (48 kHz stereo f32).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE config[1], named in config.workload): 4096 independent 48 kHz stereo streams per GPU,
+one 400 ms frame (19 200 frames) per stream per step, through the fused K-weighting + gated-RMS path
+(ebur128 modes M|S|I|LRA|HISTOGRAM: K-weighting, 100 ms energy buckets, block gating histograms,
+momentary/short-term/integrated/LRA scalars).  Meter state is carried across steps.  Under torchrun
+every rank owns its own 4096 streams (weak scaling); the only collective is the per-step all_gather of
+the per-stream result scalars (NCCL).
+
+  value      device-resident inputs, whole-job samples/s over all ranks (max-over-ranks device time)
+  e2e        the same through the host-facing C-ABI call (pinned host buffers, H2D inside the timed
+             region, result scalars read back to the host every step)
+  roofline   the dominant kernel (the K-weighting filter kernel): algorithmic 4 B/sample over its
+             CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline / --impl reference   the CPU oracle (oracle/, a restatement of the reference's algorithm;
+             the Rust reference itself cannot be built in this image) on the box's host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_STREAMS = 4096
+CHANNELS = 2
+RATE = 48000
+FRAMES = 19200  # 400 ms
+WORKLOAD = "cfg2: 4096 streams/GPU x 400 ms (19200 frames) x 48 kHz stereo f32, K-weighting + gated RMS (M|S|I|LRA|HISTOGRAM)"
+METRIC = "audio samples/sec (48 kHz stereo f32) through FFT+LUFS"
+UNIT = "samples/s"
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_input_np(n_streams, frames, seed):
+    import numpy as np
+    from tests.signals import stream_batch
+    return stream_batch(n_streams, frames, CHANNELS, seed=seed, rate=RATE)
+
+
+def make_input_device(torch, n_streams, frames, seed, device):
+    """cfg2 generator on the device: per-stream tone 100*2^((s%64)/8) Hz at 0.25 + 0.05 uniform noise."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    t = torch.arange(frames, device=device, dtype=torch.float64) / RATE
+    s = torch.arange(n_streams, device=device, dtype=torch.float64)
+    f = 100.0 * torch.pow(torch.tensor(2.0, device=device, dtype=torch.float64), (s % 64) / 8.0)
+    ph = torch.rand((n_streams, 1, CHANNELS), generator=g, device=device, dtype=torch.float64) * 6.283185307179586
+    x = 0.25 * torch.sin(6.283185307179586 * f[:, None, None] * t[None, :, None] + ph)
+    x = x + 0.05 * (torch.rand((n_streams, frames, CHANNELS), generator=g, device=device, dtype=torch.float64) * 2 - 1)
+    return x.to(torch.float32).contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [c.strip() for c in r.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx = float(p[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def cpu_oracle_run(steps, warmup, threads, n_streams=N_STREAMS, budget_s=25.0):
+    """Times the CPU oracle (loudness modes of the GPU arm) on the same workload shape.  Returns
+    (samples_per_s, ms_per_step, sample_description).  Bounded: stops adding steps past budget_s."""
+    import numpy as np
+    import oracle as O
+    x = [make_input_np(n_streams, FRAMES, seed=77 + i) for i in range(2)]
+    b = O.Batch(n_streams, CHANNELS, RATE, O.MODE_LOUDNESS)
+    for i in range(warmup):
+        b.add_frames(x[i & 1], threads=threads)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        b.add_frames(x[i & 1], threads=threads)
+        b.query(threads=threads)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    samples = done * n_streams * FRAMES * CHANNELS
+    return samples / dt, dt / done * 1e3, f"{done} step(s) of {n_streams} streams x {FRAMES} frames x {CHANNELS} ch (oracle port, modes M|S|I|LRA|HISTOGRAM, {threads} threads)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    v, ms, sample = cpu_oracle_run(max(1, args.steps), min(args.warmup, 1), threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "streams": N_STREAMS, "frames_per_step": FRAMES, "channels": CHANNELS, "rate": RATE,
+                   "note": "CPU restatement of the reference algorithm (oracle/); the Rust reference cannot be built here (no cargo/rustc, crates not vendored)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import soundscope_b200 as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, args.warmup
+    an = S.BatchAnalyzer(N_STREAMS, CHANNELS, RATE, S.MODE_LOUDNESS, device=local)
+    # two distinct 629 MB inputs, alternated: every step streams data that is not in the 126 MB L2
+    xs = [make_input_device(torch, N_STREAMS, FRAMES, 1234 + 17 * rank + i, dev) for i in range(2)]
+    res = torch.empty((N_STREAMS, an.stride), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * N_STREAMS, an.stride), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step(i):
+        an.add_frames_device(xs[i & 1])
+        an.results_device(res)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, res)
+
+    for i in range(W):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    an.profile(True)
+    l0 = an.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        step(i)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = an.launches - l0
+    filt_ms, filt_n = an.profile_read()
+    an.profile(False)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    samples_per_step = N_STREAMS * FRAMES * CHANNELS
+    value = n_gpus * samples_per_step * K / (ms_total * 1e-3)
+
+    # ---- e2e: host-facing call, pinned host inputs, H2D + result read-back inside the timed region ----
+    hx = [torch.empty((N_STREAMS, FRAMES, CHANNELS), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for i in range(2):
+        hx[i].copy_(xs[i].cpu())
+    an2 = S.BatchAnalyzer(N_STREAMS, CHANNELS, RATE, S.MODE_LOUDNESS, device=local)
+    e2e_steps = max(3, min(K, 10))
+    for i in range(2):
+        an2.add_frames_host(hx[i & 1])
+        an2.loudness_global()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        an2.add_frames_host(hx[i & 1])
+        lufs = an2.loudness_global()   # D2H read of every stream's result scalars
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = n_gpus * samples_per_step * e2e_steps / float(tt.item())
+    h2d = samples_per_step * 4
+    d2h = N_STREAMS * an2.stride * 8
+
+    # ---- optional extras: Mode::all() (adds sample + true peak) and the cfg3 FFT, device-resident ----
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        try:
+            an3 = S.BatchAnalyzer(N_STREAMS, CHANNELS, RATE, S.MODE_ALL, device=local)
+            for i in range(2):
+                an3.add_frames_device(xs[i & 1])
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            reps = 5
+            for i in range(reps):
+                an3.add_frames_device(xs[i & 1])
+            a1.record()
+            torch.cuda.synchronize()
+            extras["mode_all_samples_per_s"] = samples_per_step * reps / (a0.elapsed_time(a1) * 1e-3)
+            del an3
+            nfft, nwin = 8192, 8192
+            xf = make_input_device(torch, nwin, nfft, 99, dev)
+            out = an.fft_batch_device(xf)
+            torch.cuda.synchronize()
+            a0.record()
+            for i in range(3):
+                an.fft_batch_device(xf, out=out)
+            a1.record()
+            torch.cuda.synchronize()
+            fms = a0.elapsed_time(a1) / 3
+            nb = out.shape[2]
+            extras["fft8192_midside_windows_per_s"] = nwin / (fms * 1e-3)
+            extras["fft8192_midside_gbs"] = nwin * (nfft * 2 * 4 + 2 * nb * 4) / (fms * 1e-3) / 1e9
+        except Exception as ex:  # extras never invalidate the headline
+            extras["error"] = repr(ex)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    kern_ms = filt_ms / max(filt_n, 1)
+    achieved = (samples_per_step * 4) / (kern_ms * 1e-3) / 1e9 if filt_n else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("filter_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    # CPU baseline leg: bounded sample of the same workload on the host cores (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = host_threads()
+        v, _, sample = cpu_oracle_run(3, 1, threads, budget_s=20.0)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "streams_per_gpu": N_STREAMS, "frames_per_step": FRAMES, "channels": CHANNELS,
+                   "rate": RATE, "parallelism": f"streams sharded x{n_gpus}, all_gather of result scalars per step" if n_gpus > 1 else "single GPU",
+                   "l2": "two alternating 629 MB inputs per GPU (> 126 MB L2), no flush needed"},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_loudness (K-weighting + 100 ms energy buckets)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_launch": samples_per_step * 4},
+        "cpu_baseline": cpu,
+        "extras": extras,
+        "streams_realtime_equiv": value / (RATE * CHANNELS),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the Mode::all and FFT extras")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -159,6 +159,12 @@ int32_t ssb_mid_side(ssb_analyzer* h, const float* interleaved, size_t len, floa
 int32_t ssb_mid_side_device(ssb_analyzer* h, const float* d_interleaved, size_t len, float* d_mid,
                             float* d_side);
 
+/* ---- kernel timing (bench.py's roofline leg) ------------------------------------------------ */
+/* when enabled, every K-weighting (filter) launch is bracketed by CUDA events on the handle's stream */
+int32_t ssb_profile_enable(ssb_analyzer* h, int32_t on);
+/* synchronises, then returns and clears the accumulated filter-kernel time and launch count */
+int32_t ssb_profile_read(ssb_analyzer* h, double* filter_ms, uint64_t* filter_launches);
+
 /* ---- introspection used by the tests ------------------------------------------------------ */
 int32_t ssb_filter_coeffs(const ssb_analyzer* h, double b[5], double a[5]);
 /* copy the two 1000-bin histograms of stream s to HOST */

@@ -67,6 +67,7 @@ def lib():
         L.orc_batch_free.argtypes = [C.c_void_p]
         L.orc_batch_add_frames.argtypes = [C.c_void_p, f32p, C.c_size_t, C.c_int]
         L.orc_batch_query.argtypes = [C.c_void_p, f64p, f64p, f64p, f64p, f64p, C.c_int]
+        L.orc_batch_histograms.argtypes = [C.c_void_p, C.c_size_t, u64p, u64p]
         L.orc_cosf.restype = C.c_float
         L.orc_cosf.argtypes = [C.c_float]
         L.orc_hann_window.argtypes = [f32p, C.c_size_t, f32p]
@@ -319,6 +320,13 @@ class Batch:
         rc = lib().orc_batch_add_frames(self._h, p, frames, threads)
         if rc:
             raise OracleError(rc, "batch_add_frames")
+
+    def _per_stream_hist(self, s):
+        blk = np.zeros(1000, dtype=np.uint64)
+        st = np.zeros(1000, dtype=np.uint64)
+        p = C.POINTER(C.c_uint64)
+        lib().orc_batch_histograms(self._h, s, blk.ctypes.data_as(p), st.ctypes.data_as(p))
+        return blk, st
 
     def query(self, threads=1):
         n, ch = self.n, self.channels

@@ -516,6 +516,10 @@ int orc_batch_add_frames(orc_batch* b, const float* in, size_t frames, int threa
   return rc_all;
 }
 
+void orc_batch_histograms(orc_batch* b, size_t s, uint64_t block[1000], uint64_t shortterm[1000]) {
+  orc_ebur128_histograms(b->st[s], block, shortterm);
+}
+
 void orc_batch_query(orc_batch* b, double* momentary, double* shortterm, double* global,
                      double* range, double* true_peak, int threads) {
 #pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)

@@ -85,6 +85,7 @@ typedef struct orc_batch orc_batch;
 orc_batch* orc_batch_new(size_t n_streams, uint32_t channels, uint32_t rate, int mode);
 void orc_batch_free(orc_batch* b);
 int orc_batch_add_frames(orc_batch* b, const float* in, size_t frames, int threads);
+void orc_batch_histograms(orc_batch* b, size_t s, uint64_t block[1000], uint64_t shortterm[1000]);
 void orc_batch_query(orc_batch* b, double* momentary, double* shortterm, double* global,
                      double* range, double* true_peak /* n*channels */, int threads);
 

@@ -46,7 +46,7 @@ SYMBOLS = [
     "ssb_true_peak", "ssb_sample_peak", "ssb_get_true_peak", "ssb_result_stride", "ssb_results_device",
     "ssb_calculate_integrated_lufs", "ssb_get_fft", "ssb_fft_bins", "ssb_fft_axis", "ssb_fft_batch_device",
     "ssb_get_waveform", "ssb_waveform_device", "ssb_mid_side", "ssb_mid_side_device", "ssb_filter_coeffs",
-    "ssb_histograms",
+    "ssb_histograms", "ssb_profile_enable", "ssb_profile_read",
 ]
 
 _lib = None
@@ -103,6 +103,8 @@ def lib():
         "ssb_mid_side_device": (C.c_int32, [vp, f32p, C.c_size_t, f32p, f32p]),
         "ssb_filter_coeffs": (C.c_int32, [vp, f64p, f64p]),
         "ssb_histograms": (C.c_int32, [vp, C.c_size_t, vp, vp]),
+        "ssb_profile_enable": (C.c_int32, [vp, C.c_int32]),
+        "ssb_profile_read": (C.c_int32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():

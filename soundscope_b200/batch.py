@@ -38,6 +38,15 @@ class BatchAnalyzer:
     def launches(self):
         return lib().ssb_launch_count(self._h)
 
+    def profile(self, on=True):
+        check(self._h, lib().ssb_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """(total filter-kernel ms, launches) since the last read; CUDA-event time on the handle's stream."""
+        ms, n = C.c_double(0), C.c_uint64(0)
+        check(self._h, lib().ssb_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def sync(self):
         check(self._h, lib().ssb_sync(self._h))
 

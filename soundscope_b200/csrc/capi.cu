@@ -45,6 +45,9 @@ struct ssb_analyzer {
   std::map<std::pair<size_t, uint32_t>, std::pair<std::vector<double>, std::vector<double>>> axes;
 
   uint64_t launches = 0;
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
   char err[256] = {0};
 };
 
@@ -189,8 +192,21 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
     const uint64_t bucket0 = h->total_frames / s100;
     const size_t max_frames = (size_t)kMaxBucketsPerLaunch * s100 - pos;
     const size_t n = frames - done < max_frames ? frames - done : max_frames;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (h->profiling) {
+      if (h->prof_used == h->prof_events.size()) {
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
+        h->prof_events.emplace_back(ev0, ev1);
+      }
+      ev0 = h->prof_events[h->prof_used].first;
+      ev1 = h->prof_events[h->prof_used].second;
+      h->prof_used++;
+      CK(cudaEventRecord(ev0, h->stream));
+    }
     CK(launch_loudness_generic(h->lp, h->st, d_in + done * C, n, in_stride_frames, pos, bucket0, h->ring_pos,
                                h->stream, &h->launches));
+    if (ev1) CK(cudaEventRecord(ev1, h->stream));
     const uint64_t completed = (pos + n) / s100;
     if (completed) CK(launch_gating(h->gp, h->st, bucket0, bucket0 + completed - 1, h->stream, &h->launches));
     h->total_frames += n;
@@ -321,6 +337,10 @@ void ssb_analyzer_destroy(ssb_analyzer* h) {
   }
   cudaFree(h->d_scratch);
   if (h->h_scratch) cudaFreeHost(h->h_scratch);
+  for (auto& ev : h->prof_events) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
   for (auto& kv : h->plans) {
     cudaFree(kv.second.d_window);
     cudaFree(kv.second.d_twiddle);
@@ -717,6 +737,31 @@ int32_t ssb_mid_side(ssb_analyzer* h, const float* interleaved, size_t len, floa
   CK(cudaMemcpyAsync(mid, d_mid, half, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(side, d_side, half, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return SSB_OK;
+}
+
+int32_t ssb_profile_enable(ssb_analyzer* h, int32_t on) {
+  if (!h) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  h->profiling = on != 0;
+  h->prof_used = 0;
+  return SSB_OK;
+}
+
+int32_t ssb_profile_read(ssb_analyzer* h, double* filter_ms, uint64_t* filter_launches) {
+  if (!h || !filter_ms || !filter_launches) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  double total = 0.0;
+  for (size_t i = 0; i < h->prof_used; i++) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->prof_events[i].first, h->prof_events[i].second));
+    total += ms;
+  }
+  *filter_ms = total;
+  *filter_launches = h->prof_used;
+  h->prof_used = 0;
   return SSB_OK;
 }
 

@@ -1,0 +1,265 @@
+"""GPU parity: the CUDA loudness path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): LUFS within 1e-4 LU (the f64 paths agree to ~1e-12 in practice;
+the test asserts 1e-9 where no histogram quantisation is involved and exact histogram equality where it
+is); true peak within 2e-6 relative (f32 polyphase FIR, FMA vs separate multiply-add; the crate's own
+accumulation order is not pinned — see DESIGN.md).
+"""
+import numpy as np
+import pytest
+
+from tests.signals import stream_batch, sweep_stereo
+
+pytestmark = pytest.mark.gpu
+
+LU_TOL = 1e-4
+TP_RTOL = 2e-6
+
+
+def close_lu(a, b, tol=LU_TOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    both_inf = np.isneginf(a) & np.isneginf(b)
+    return np.all(both_inf | (np.abs(a - b) <= tol))
+
+
+def oracle_batch(oracle, x, rate, mode, chunks=None):
+    n, frames, ch = x.shape
+    b = oracle.Batch(n, ch, rate, mode)
+    if chunks is None:
+        b.add_frames(x)
+    else:
+        off = 0
+        for c in chunks:
+            b.add_frames(np.ascontiguousarray(x[:, off:off + c, :]))
+            off += c
+    return b
+
+
+def test_reference_tests_on_gpu(ssb, oracle, cuda):
+    """The reference's own loudness unit tests (analyzer.rs:362-398) against the CUDA Analyzer."""
+    a = ssb.Analyzer()
+    i = np.arange(88200, dtype=np.float32)
+    s = (np.float32(0.1) * np.sin(np.float32(440.0) * np.float32(2.0) * np.float32(np.pi) * (i / np.float32(44100.0)))).astype(np.float32)
+    a.add_samples(s)
+    lufs = a.get_integrated_lufs()
+    assert -100.0 < lufs < 0.0
+    l, r = a.get_true_peak()
+    assert 0.0 <= l <= 1.0 and 0.0 <= r <= 1.0
+    o = oracle.Analyzer()
+    o.add_samples(s)
+    assert abs(lufs - o.get_integrated_lufs()) <= LU_TOL
+    assert abs(a.get_shortterm_lufs() - o.get_shortterm_lufs()) <= LU_TOL
+    ol, orr = o.get_true_peak()
+    assert abs(l - ol) <= TP_RTOL * ol and abs(r - orr) <= TP_RTOL * orr
+    # test_analyzer_reinit
+    a.create_loudness_meter(1, 48000)
+    a.create_loudness_meter(6, 96000)
+    for ch, rate in ((0, 48000), (65, 48000), (2, 15), (2, 2822401)):
+        with pytest.raises(ssb.SsbError) as e:
+            a.create_loudness_meter(ch, rate)
+        assert e.value.code == 1  # Error::NoMem
+    a.create_loudness_meter(1, 48000)
+    with pytest.raises(ssb.SsbError) as e:
+        a.get_true_peak()
+    assert e.value.code == 3  # Error::InvalidChannelIndex
+
+
+def test_player_tick_shape_single_stream(ssb, oracle, cuda):
+    """tui.rs:1528-1543: overlapping 16384-sample windows every 2048 samples, short-term query after each."""
+    x = sweep_stereo(6.0, 48000)
+    a, o = ssb.Analyzer(), oracle.Analyzer()
+    a.create_loudness_meter(2, 48000)
+    o.create_loudness_meter(2, 48000)
+    got, want = [], []
+    for pos in range(16384 + 2048, x.size, 2048 * 12):
+        a.add_samples(x[pos - 16384:pos])
+        o.add_samples(x[pos - 16384:pos])
+        got.append(a.get_shortterm_lufs())
+        want.append(o.get_shortterm_lufs())
+    assert close_lu(got, want, 1e-9)
+    assert abs(a.get_integrated_lufs() - o.get_integrated_lufs()) <= LU_TOL
+    assert abs(a.get_loudness_range() - o.get_loudness_range()) <= LU_TOL
+    bg, sg = a.histograms()
+    bo, so = o._meter.histograms()
+    assert np.array_equal(bg, bo) and np.array_equal(sg, so)
+    assert abs(a.get_momentary_lufs() - o._meter.loudness_momentary()) <= 1e-9
+    a.reset()
+    o.reset()
+    assert a.get_integrated_lufs() == -np.inf and a.get_shortterm_lufs() == -np.inf
+    assert a.get_loudness_range() == 0.0 and a.get_true_peak() == (0.0, 0.0)
+    a.add_samples(x[:48000])
+    o.add_samples(x[:48000])
+    assert abs(a.get_shortterm_lufs() - o.get_shortterm_lufs()) <= 1e-9
+
+
+def test_random_chunking_single_stream(ssb, oracle, cuda):
+    x = sweep_stereo(5.0, 44100)
+    a, o = ssb.Analyzer(), oracle.Analyzer()
+    rng = np.random.default_rng(11)
+    off = 0
+    while off < x.size:
+        n = 2 * int(rng.integers(1, 30000))
+        a.add_samples(x[off:off + n])
+        o.add_samples(x[off:off + n])
+        off += n
+        if rng.integers(0, 3) == 0:
+            assert abs(a.get_shortterm_lufs() - o.get_shortterm_lufs()) <= 1e-9
+    assert abs(a.get_integrated_lufs() - o.get_integrated_lufs()) <= LU_TOL
+    assert np.array_equal(a.histograms()[0], o._meter.histograms()[0])
+    l, r = a.get_true_peak()
+    ol, orr = o.get_true_peak()
+    assert abs(l - ol) <= TP_RTOL * ol and abs(r - orr) <= TP_RTOL * orr
+
+
+def test_calculate_integrated_lufs(ssb, oracle, cuda):
+    x = sweep_stereo(10.0, 48000)
+    a, o = ssb.Analyzer(), oracle.Analyzer()
+    a.create_loudness_meter(2, 48000)
+    o.create_loudness_meter(2, 48000)
+    assert abs(a.calculate_integrated_lufs(2, x) - o.calculate_integrated_lufs(2, x)) <= LU_TOL
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "golden_v1.npz"))
+    assert abs(a.calculate_integrated_lufs(2, x) - g["sweep_integrated_oneshot"][0]) <= LU_TOL
+    assert a.calculate_integrated_lufs(2, np.zeros(48000 * 2 + 1, dtype=np.float32)) is None
+    assert a.calculate_integrated_lufs(0, x[:100]) is None
+    assert a.calculate_integrated_lufs(2, np.zeros(0, dtype=np.float32)) == -np.inf
+    # channels = 1 with the reference's stereo-sized chunking
+    assert abs(a.calculate_integrated_lufs(1, x[:96000 * 3]) - o.calculate_integrated_lufs(1, x[:96000 * 3])) <= LU_TOL
+
+
+def test_add_samples_ragged_and_empty(ssb, cuda):
+    a = ssb.Analyzer()
+    a.add_samples(np.zeros(0, dtype=np.float32))
+    with pytest.raises(ssb.SsbError) as e:
+        a.add_samples(np.zeros(3, dtype=np.float32))
+    assert e.value.code == 1
+    assert a.get_integrated_lufs() == -np.inf
+
+
+@pytest.mark.parametrize("channels,rate", [(1, 48000), (2, 44100), (2, 48000), (4, 48000), (5, 48000), (6, 96000),
+                                           (2, 192000), (2, 8000), (3, 22050), (8, 48000)])
+def test_batch_parity_channels_rates(ssb, oracle, cuda, channels, rate):
+    torch = cuda
+    n = 24
+    frames = int(rate * 3.7) + 13
+    x = stream_batch(n, frames, channels, seed=channels * 1000 + rate % 997, rate=rate)
+    mode = ssb.MODE_ALL
+    chunks = [frames // 3 + 5, frames // 2 - 7]
+    chunks.append(frames - sum(chunks))
+    ob = oracle_batch(oracle, x, rate, mode, chunks)
+    want = ob.query()
+    b = ssb.BatchAnalyzer(n, channels, rate, mode, flags=ssb.FLAG_RING)
+    xd = torch.from_numpy(x).cuda()
+    off = 0
+    for c in chunks:
+        b.add_frames_device(xd[:, off:off + c, :].contiguous())
+        off += c
+    assert close_lu(b.loudness_momentary(), want["momentary"], 1e-9)
+    assert close_lu(b.loudness_shortterm(), want["shortterm"], 1e-9)
+    assert close_lu(b.loudness_global(), want["global"])
+    assert close_lu(b.loudness_range(), want["range"])
+    tp = b.true_peak()
+    assert np.all(np.abs(tp - want["true_peak"]) <= TP_RTOL * np.maximum(want["true_peak"], 1e-30))
+    for s in (0, n - 1):
+        hb, hs = b.histograms(s)
+        ob_b, ob_s = ob._per_stream_hist(s)
+        assert np.array_equal(hb, ob_b) and np.array_equal(hs, ob_s)
+
+
+def test_block_mode_matches_ring_mode_on_grid(ssb, oracle, cuda):
+    """Without SSB_FLAG_RING the handle keeps only 100 ms energy sums: queries on the grid agree with the
+    oracle, queries off the grid are refused (SSB_ERR_UNALIGNED_QUERY), integrated/LRA/peaks always work."""
+    torch = cuda
+    n, rate, ch = 16, 48000, 2
+    x = stream_batch(n, 4800 * 37 + 1234, ch, seed=77)
+    b = ssb.BatchAnalyzer(n, ch, rate, ssb.MODE_ALL)
+    xd = torch.from_numpy(x).cuda()
+    b.add_frames_device(xd[:, :4800 * 37, :].contiguous())
+    ob = oracle.Batch(n, ch, rate, oracle.MODE_ALL)
+    ob.add_frames(np.ascontiguousarray(x[:, :4800 * 37, :]))
+    want = ob.query()
+    assert close_lu(b.loudness_momentary(), want["momentary"], 1e-9)
+    assert close_lu(b.loudness_shortterm(), want["shortterm"], 1e-9)
+    assert close_lu(b.loudness_global(), want["global"])
+    b.add_frames_device(xd[:, 4800 * 37:, :].contiguous())
+    ob.add_frames(np.ascontiguousarray(x[:, 4800 * 37:, :]))
+    want = ob.query()
+    for q in (b.loudness_momentary, b.loudness_shortterm):
+        with pytest.raises(ssb.SsbError) as e:
+            q()
+        assert e.value.code == 12
+    assert close_lu(b.loudness_global(), want["global"])
+    assert close_lu(b.loudness_range(), want["range"])
+    assert np.all(np.abs(b.true_peak() - want["true_peak"]) <= TP_RTOL * want["true_peak"])
+
+
+def test_modes(ssb, oracle, cuda):
+    torch = cuda
+    n, rate, ch = 8, 48000, 2
+    x = stream_batch(n, 48000 * 4, ch, seed=5)
+    xd = torch.from_numpy(x).cuda()
+    b = ssb.BatchAnalyzer(n, ch, rate, ssb.MODE_LOUDNESS)
+    b.add_frames_device(xd)
+    ob = oracle.Batch(n, ch, rate, oracle.MODE_LOUDNESS)
+    ob.add_frames(x)
+    want = ob.query()
+    assert close_lu(b.loudness_global(), want["global"]) and close_lu(b.loudness_shortterm(), want["shortterm"], 1e-9)
+    for q in (b.true_peak, b.sample_peak):
+        with pytest.raises(ssb.SsbError) as e:
+            q()
+        assert e.value.code == 2
+    m = ssb.BatchAnalyzer(n, ch, rate, ssb.MODE_M)
+    m.add_frames_device(xd)
+    om = oracle.Batch(n, ch, rate, oracle.MODE_M)
+    om.add_frames(x)
+    assert close_lu(m.loudness_momentary(), om.query()["momentary"], 1e-9)
+    for q in (m.loudness_shortterm, m.loudness_global, m.loudness_range):
+        with pytest.raises(ssb.SsbError) as e:
+            q()
+        assert e.value.code == 2
+    with pytest.raises(ssb.SsbError):
+        ssb.BatchAnalyzer(n, ch, rate, ssb.MODE_I)  # integrated without HISTOGRAM is not the analyzer's mode
+
+
+def test_host_and_device_feeds_agree_bitwise(ssb, cuda):
+    torch = cuda
+    n, rate, ch = 32, 48000, 2
+    x = stream_batch(n, 19200 * 3, ch, seed=9)
+    a = ssb.BatchAnalyzer(n, ch, rate)
+    b = ssb.BatchAnalyzer(n, ch, rate)
+    xd = torch.from_numpy(x).cuda()
+    pin = torch.from_numpy(x).pin_memory()
+    for k in range(3):
+        a.add_frames_device(xd[:, k * 19200:(k + 1) * 19200, :].contiguous())
+        b.add_frames_host(pin[:, k * 19200:(k + 1) * 19200, :].contiguous())
+    ra, rb = a.results_device().cpu().numpy(), b.results_device().cpu().numpy()
+    assert np.array_equal(ra, rb, equal_nan=True)
+    # stream independence: stream s of the batch equals a 1-stream handle fed the same slice
+    s = 17
+    one = ssb.BatchAnalyzer(1, ch, rate)
+    one.add_frames_device(xd[s:s + 1].contiguous())
+    assert np.array_equal(one.results_device().cpu().numpy()[0], ra[s], equal_nan=True)
+
+
+def test_cfg2_full_size_properties(ssb, oracle, cuda):
+    """BASELINE config 2 at full size (4096 streams x 400 ms x 25 launches): oracle on a subset of streams,
+    size-independent properties on all of them (gain linearity of the momentary level, stream independence)."""
+    torch = cuda
+    n, rate, ch, frames = 4096, 48000, 2, 19200
+    b = ssb.BatchAnalyzer(n, ch, rate, ssb.MODE_LOUDNESS)
+    b2 = ssb.BatchAnalyzer(n, ch, rate, ssb.MODE_LOUDNESS)
+    sub = np.arange(0, n, 331)
+    ob = oracle.Batch(len(sub), ch, rate, oracle.MODE_LOUDNESS)
+    for k in range(25):
+        x = stream_batch(n, frames, ch, seed=1000 + k, t0=k * frames)
+        xd = torch.from_numpy(x).cuda()
+        b.add_frames_device(xd)
+        b2.add_frames_device((xd * 2.0).contiguous())
+        ob.add_frames(np.ascontiguousarray(x[sub]))
+    want = ob.query()
+    m1, m2 = b.loudness_momentary(), b2.loudness_momentary()
+    assert close_lu(m1[sub], want["momentary"], 1e-9)
+    assert close_lu(b.loudness_shortterm()[sub], want["shortterm"], 1e-9)
+    assert close_lu(b.loudness_global()[sub], want["global"])
+    assert close_lu(b.loudness_range()[sub], want["range"])
+    assert np.allclose(m2 - m1, 20 * np.log10(2.0), rtol=0, atol=1e-9)   # exact doubling -> +6.0206 LU
+    assert np.all(np.isfinite(b.loudness_global()))
