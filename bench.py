@@ -130,7 +130,7 @@ def cpu_oracle_run(steps, warmup, threads, n_streams=N_STREAMS, budget_s=25.0):
     import numpy as np
     import oracle as O
     x = [make_input_np(n_streams, FRAMES, seed=77 + i) for i in range(2)]
-    b = O.Batch(n_streams, CHANNELS, RATE, O.MODE_LOUDNESS)
+    b = O.Batch(n_streams, CHANNELS, RATE, O.MODE_LOUDNESS, threads=threads)
     for i in range(warmup):
         b.add_frames(x[i & 1], threads=threads)
     t0 = time.perf_counter()

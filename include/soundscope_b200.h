@@ -93,8 +93,10 @@ uint32_t ssb_channels(const ssb_analyzer* h);
 size_t ssb_n_streams(const ssb_analyzer* h);
 /* last error text of this handle (never NULL) */
 const char* ssb_last_error(const ssb_analyzer* h);
-/* run this handle's work on a caller-owned CUDA stream (cudaStream_t); NULL restores the handle's own */
+/* run this handle's work on a caller-owned CUDA stream (cudaStream_t; NULL is the CUDA default stream) */
 int32_t ssb_set_stream(ssb_analyzer* h, void* cuda_stream);
+/* go back to the handle's own non-blocking stream (the state after create) */
+int32_t ssb_use_own_stream(ssb_analyzer* h);
 int32_t ssb_sync(ssb_analyzer* h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 uint64_t ssb_launch_count(const ssb_analyzer* h);
@@ -164,6 +166,9 @@ int32_t ssb_mid_side_device(ssb_analyzer* h, const float* d_interleaved, size_t 
 int32_t ssb_profile_enable(ssb_analyzer* h, int32_t on);
 /* synchronises, then returns and clears the accumulated filter-kernel time and launch count */
 int32_t ssb_profile_read(ssb_analyzer* h, double* filter_ms, uint64_t* filter_launches);
+
+/* tests only: route every add_frames through the generic (thread-per-channel) kernel */
+int32_t ssb_debug_force_generic(ssb_analyzer* h, int32_t on);
 
 /* ---- introspection used by the tests ------------------------------------------------------ */
 int32_t ssb_filter_coeffs(const ssb_analyzer* h, double b[5], double a[5]);

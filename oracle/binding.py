@@ -64,6 +64,8 @@ def lib():
         L.orc_calculate_integrated_lufs.argtypes = [C.c_uint32, C.c_uint32, f32p, C.c_size_t, f64p]
         L.orc_batch_new.restype = C.c_void_p
         L.orc_batch_new.argtypes = [C.c_size_t, C.c_uint32, C.c_uint32, C.c_int]
+        L.orc_batch_new_mt.restype = C.c_void_p
+        L.orc_batch_new_mt.argtypes = [C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
         L.orc_batch_free.argtypes = [C.c_void_p]
         L.orc_batch_add_frames.argtypes = [C.c_void_p, f32p, C.c_size_t, C.c_int]
         L.orc_batch_query.argtypes = [C.c_void_p, f64p, f64p, f64p, f64p, f64p, C.c_int]
@@ -301,8 +303,8 @@ def histogram_boundary(i):
 class Batch:
     """n independent meters — the timed CPU baseline (bench.py) and batch parity checker."""
 
-    def __init__(self, n_streams, channels, rate, mode=MODE_ALL):
-        self._h = lib().orc_batch_new(n_streams, channels, rate, mode)
+    def __init__(self, n_streams, channels, rate, mode=MODE_ALL, threads=1):
+        self._h = lib().orc_batch_new_mt(n_streams, channels, rate, mode, threads)
         if not self._h:
             raise OracleError(ERR_NOMEM, "batch_new")
         self.n, self.channels, self.rate, self.mode = n_streams, channels, rate, mode

@@ -488,16 +488,25 @@ struct orc_batch {
 };
 
 orc_batch* orc_batch_new(size_t n_streams, uint32_t channels, uint32_t rate, int mode) {
+  return orc_batch_new_mt(n_streams, channels, rate, mode, 1);
+}
+
+/* `threads` > 1: meters are created (first-touched) by the thread that will later process them,
+ * with the same static schedule, so each meter's ring lives on its worker's NUMA node. */
+orc_batch* orc_batch_new_mt(size_t n_streams, uint32_t channels, uint32_t rate, int mode, int threads) {
   orc_batch* b = (orc_batch*)calloc(1, sizeof(*b));
   if (!b) return NULL;
   b->n = n_streams;
   b->channels = channels;
   b->st = (orc_ebur128**)calloc(n_streams, sizeof(orc_ebur128*));
-  for (size_t i = 0; i < n_streams; i++) {
+  int bad = 0;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1) reduction(| : bad)
+  for (long i = 0; i < (long)n_streams; i++) {
     int err;
     b->st[i] = orc_ebur128_new(channels, rate, mode, &err);
-    if (!b->st[i]) { orc_batch_free(b); return NULL; }
+    if (!b->st[i]) bad |= 1;
   }
+  if (bad) { orc_batch_free(b); return NULL; }
   return b;
 }
 

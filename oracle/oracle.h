@@ -83,6 +83,7 @@ int orc_calculate_integrated_lufs(uint32_t channels, uint32_t sample_rate, const
  * stream s reads in[s*frames*channels ..]; OpenMP over streams when threads > 1. */
 typedef struct orc_batch orc_batch;
 orc_batch* orc_batch_new(size_t n_streams, uint32_t channels, uint32_t rate, int mode);
+orc_batch* orc_batch_new_mt(size_t n_streams, uint32_t channels, uint32_t rate, int mode, int threads);
 void orc_batch_free(orc_batch* b);
 int orc_batch_add_frames(orc_batch* b, const float* in, size_t frames, int threads);
 void orc_batch_histograms(orc_batch* b, size_t s, uint64_t block[1000], uint64_t shortterm[1000]);

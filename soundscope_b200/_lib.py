@@ -40,13 +40,13 @@ class SsbError(RuntimeError):
 # every symbol include/soundscope_b200.h declares; tests/test_abi.py checks the .so exports each one
 SYMBOLS = [
     "ssb_abi_version", "ssb_analyzer_create", "ssb_analyzer_destroy", "ssb_create_loudness_meter",
-    "ssb_sample_rate", "ssb_channels", "ssb_n_streams", "ssb_last_error", "ssb_set_stream", "ssb_sync",
+    "ssb_sample_rate", "ssb_channels", "ssb_n_streams", "ssb_last_error", "ssb_set_stream", "ssb_use_own_stream", "ssb_sync",
     "ssb_launch_count", "ssb_add_frames_f32", "ssb_add_frames_f32_device", "ssb_add_samples", "ssb_reset",
     "ssb_loudness_momentary", "ssb_loudness_shortterm", "ssb_loudness_global", "ssb_loudness_range",
     "ssb_true_peak", "ssb_sample_peak", "ssb_get_true_peak", "ssb_result_stride", "ssb_results_device",
     "ssb_calculate_integrated_lufs", "ssb_get_fft", "ssb_fft_bins", "ssb_fft_axis", "ssb_fft_batch_device",
     "ssb_get_waveform", "ssb_waveform_device", "ssb_mid_side", "ssb_mid_side_device", "ssb_filter_coeffs",
-    "ssb_histograms", "ssb_profile_enable", "ssb_profile_read",
+    "ssb_histograms", "ssb_profile_enable", "ssb_profile_read", "ssb_debug_force_generic",
 ]
 
 _lib = None
@@ -77,6 +77,7 @@ def lib():
         "ssb_n_streams": (C.c_size_t, [vp]),
         "ssb_last_error": (C.c_char_p, [vp]),
         "ssb_set_stream": (C.c_int32, [vp, vp]),
+        "ssb_use_own_stream": (C.c_int32, [vp]),
         "ssb_sync": (C.c_int32, [vp]),
         "ssb_launch_count": (C.c_uint64, [vp]),
         "ssb_add_frames_f32": (C.c_int32, [vp, f32p, C.c_size_t]),
@@ -104,6 +105,7 @@ def lib():
         "ssb_filter_coeffs": (C.c_int32, [vp, f64p, f64p]),
         "ssb_histograms": (C.c_int32, [vp, C.c_size_t, vp, vp]),
         "ssb_profile_enable": (C.c_int32, [vp, C.c_int32]),
+        "ssb_debug_force_generic": (C.c_int32, [vp, C.c_int32]),
         "ssb_profile_read": (C.c_int32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     }
     assert set(sig) == set(SYMBOLS)

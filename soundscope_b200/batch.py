@@ -38,6 +38,9 @@ class BatchAnalyzer:
     def launches(self):
         return lib().ssb_launch_count(self._h)
 
+    def force_generic(self, on=True):
+        check(self._h, lib().ssb_debug_force_generic(self._h, 1 if on else 0))
+
     def profile(self, on=True):
         check(self._h, lib().ssb_profile_enable(self._h, 1 if on else 0))
 

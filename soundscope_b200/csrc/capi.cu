@@ -45,6 +45,7 @@ struct ssb_analyzer {
   std::map<std::pair<size_t, uint32_t>, std::pair<std::vector<double>, std::vector<double>>> axes;
 
   uint64_t launches = 0;
+  bool force_generic = false;  // tests: route everything through the generic kernel
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
@@ -204,8 +205,15 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
       h->prof_used++;
       CK(cudaEventRecord(ev0, h->stream));
     }
-    CK(launch_loudness_generic(h->lp, h->st, d_in + done * C, n, in_stride_frames, pos, bucket0, h->ring_pos,
-                               h->stream, &h->launches));
+    size_t tiled = 0;
+    if (!h->force_generic && tile_path_usable(h->lp, h->st, d_in + done * C, n, in_stride_frames))
+      CK(launch_loudness_tile(h->lp, h->st, d_in + done * C, n, in_stride_frames, pos, bucket0, h->stream,
+                              &h->launches, &tiled));
+    if (tiled < n) {
+      const uint64_t t2 = h->total_frames + tiled;
+      CK(launch_loudness_generic(h->lp, h->st, d_in + (done + tiled) * C, n - tiled, in_stride_frames,
+                                 (uint32_t)(t2 % s100), t2 / s100, h->ring_pos, h->stream, &h->launches));
+    }
     if (ev1) CK(cudaEventRecord(ev1, h->stream));
     const uint64_t completed = (pos + n) / s100;
     if (completed) CK(launch_gating(h->gp, h->st, bucket0, bucket0 + completed - 1, h->stream, &h->launches));
@@ -370,7 +378,15 @@ int32_t ssb_set_stream(ssb_analyzer* h, void* cuda_stream) {
   if (!h) return SSB_ERR_INVALID_ARG;
   DeviceGuard g(h->device);
   CK(cudaStreamSynchronize(h->stream));
-  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  h->stream = (cudaStream_t)cuda_stream;
+  return SSB_OK;
+}
+
+int32_t ssb_use_own_stream(ssb_analyzer* h) {
+  if (!h) return SSB_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  h->stream = h->own_stream;
   return SSB_OK;
 }
 
@@ -737,6 +753,12 @@ int32_t ssb_mid_side(ssb_analyzer* h, const float* interleaved, size_t len, floa
   CK(cudaMemcpyAsync(mid, d_mid, half, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(side, d_side, half, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return SSB_OK;
+}
+
+int32_t ssb_debug_force_generic(ssb_analyzer* h, int32_t on) {
+  if (!h) return SSB_ERR_INVALID_ARG;
+  h->force_generic = on != 0;
   return SSB_OK;
 }
 

@@ -70,6 +70,13 @@ struct LoudState {
 cudaError_t launch_loudness_generic(const LoudParams& p, const LoudState& st, const float* d_in,
                                     size_t frames, size_t in_stride_frames, uint32_t pos0,
                                     uint64_t bucket0, size_t ring_pos, cudaStream_t s, uint64_t* launches);
+// TMA-tiled, time-segmented fast path (loudness_tile.cu): mono/stereo, no ring, no true peak.  Consumes the
+// leading whole tiles of the chunk; the caller sends the remainder through the generic kernel.
+bool tile_path_usable(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
+                      size_t in_stride_frames);
+cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
+                                 size_t in_stride_frames, uint32_t pos0, uint64_t bucket0, cudaStream_t s,
+                                 uint64_t* launches, size_t* consumed);
 // Gating for buckets [j_first, j_last] completed by the preceding filter launch.
 cudaError_t launch_gating(const GateParams& g, const LoudState& st, uint64_t j_first, uint64_t j_last,
                           cudaStream_t s, uint64_t* launches);
