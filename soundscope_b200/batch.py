@@ -80,10 +80,10 @@ class BatchAnalyzer:
         check(self._h, lib().ssb_results_device(self._h, C.c_void_p(out.data_ptr())))
         return out
 
-    def _col(self, fn, width=1):
-        out = np.empty(self.n_streams * width, dtype=np.float64)
+    def _col(self, fn, width=None):
+        out = np.empty(self.n_streams * (width or 1), dtype=np.float64)
         check(self._h, fn(self._h, out.ctypes.data))
-        return out if width == 1 else out.reshape(self.n_streams, width)
+        return out if width is None else out.reshape(self.n_streams, width)
 
     def loudness_momentary(self):
         return self._col(lib().ssb_loudness_momentary)

@@ -15,6 +15,7 @@
 //     shared-memory tile, so HBM traffic stays at the algorithmic 4 B/sample.
 //   * bucket sums are reduced across segments in a fixed order (deterministic, no atomics).
 #include <cuda.h>
+#include <math.h>
 #include <string.h>
 
 #include "ssb_internal.cuh"
@@ -29,7 +30,7 @@ constexpr int kStages = 3;
 struct TileArgs {
   double a[5];
   double b[5];
-  double P[16];        // A^Ls, row-major
+  double P[16];        // D * A^Ls * D (state hand-off matrix in difference coordinates), row-major
   const float* in;     // unused by the TMA path (kept for debugging)
   double* filt;        // [n][C][4]
   double* bucket;      // [n][C][kNB]
@@ -92,6 +93,31 @@ __device__ __forceinline__ double widen(float x) {
   return __hiloint2double((int)hi, (int)(u << 29));
 }
 
+// d = D v with D = [[1,0,0,0],[1,-1,0,0],[1,-2,1,0],[1,-3,3,-1]] (finite differences; D is its own inverse).
+// Differences of neighbouring state samples are (nearly) exact in floating point, and the hand-off matrix
+// D A^Ls D acts on the small differences instead of cancelling four huge, nearly equal terms.
+__device__ __forceinline__ void to_diff(double v1, double v2, double v3, double v4, double& d0, double& d1,
+                                        double& d2, double& d3) {
+  const double e1 = v1 - v2, e2 = v2 - v3, e3 = v3 - v4;
+  d0 = v1;
+  d1 = e1;
+  d2 = e1 - e2;
+  d3 = (e1 - e2) - (e2 - e3);
+}
+__device__ __forceinline__ void from_diff(double d0, double d1, double d2, double d3, double& v1, double& v2,
+                                          double& v3, double& v4) {
+  const double e2 = d1 - d2;
+  const double e3 = e2 - (d2 - d3);
+  v1 = d0;
+  v2 = d0 - d1;
+  v3 = v2 - e2;
+  v4 = v3 - e3;
+}
+__device__ __forceinline__ void store_carry(double* cr, double v1, double v2, double v3, double v4) {
+  cr[0] = v1; cr[1] = v2; cr[2] = v3; cr[3] = v4;
+  to_diff(v1, v2, v3, v4, cr[4], cr[5], cr[6], cr[7]);
+}
+
 template <int C>
 __device__ __forceinline__ float pick(const float4& q, int f, int c) {
   // element (frame f of the quad, channel c); C frames-per-quad = 4 / C
@@ -118,8 +144,8 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const TileArgs a) {
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stages = smem;                                                 // kStages * STAGE_BYTES
   double* zbuf = reinterpret_cast<double*>(smem + kStages * STAGE_BYTES);       // [2][T][RC][4]
-  double* carry = zbuf + 2 * T * RC * 4;                                        // [2][RC][4]
-  double* part = carry + 2 * RC * 4;                                            // [2][T][RC][2]
+  double* carry = zbuf + 2 * T * RC * 4;                                        // [2][RC][8]: raw v1..v4 | D v
+  double* part = carry + 2 * RC * 8;                                            // [2][T][RC][2]
   float* pk = reinterpret_cast<float*>(part + 2 * T * RC * 2);                  // [T][RC]
   uint64_t* full = reinterpret_cast<uint64_t*>(pk + T * RC);                    // [kStages]
   uint64_t* empty = full + kStages;                                             // [kStages]
@@ -172,8 +198,7 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const TileArgs a) {
       const double* f = a.filt + gidx * 4;
       s0 = make_double4(f[0], f[1], f[2], f[3]);
     }
-    double* cr = carry + (size_t)rc * 4;
-    cr[0] = s0.x; cr[1] = s0.y; cr[2] = s0.z; cr[3] = s0.w;
+    store_carry(carry + (size_t)rc * 8, s0.x, s0.y, s0.z, s0.w);
   }
   double acc_cur = 0.0;   // k == 0 only: running sum of the bucket in progress
   unsigned slot = a.slot0;
@@ -215,19 +240,30 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const TileArgs a) {
           }
         }
       }
-      double* zp = zbuf + (((size_t)par * T + k) * RC + rc) * 4;
-      zp[0] = z1; zp[1] = z2; zp[2] = z3; zp[3] = z4;
+      {
+        // hand-off runs in difference coordinates d = D v (see to_diff): the DF-II state is four consecutive
+        // samples of a large, smooth internal signal, and A^Ls applied to it directly cancels ~1e3-fold
+        double* zp = zbuf + (((size_t)par * T + k) * RC + rc) * 4;
+        double d0, d1, d2, d3;
+        to_diff(z1, z2, z3, z4, d0, d1, d2, d3);
+        zp[0] = d0; zp[1] = d1; zp[2] = d2; zp[3] = d3;
+      }
       bar_sync_compute(NC);
       // ---- combine: true incoming state of segment k ----
-      const double* cr = carry + ((size_t)par * RC + rc) * 4;
-      v1 = cr[0]; v2 = cr[1]; v3 = cr[2]; v4 = cr[3];
-      for (int j = 0; j < k; j++) {
-        const double* zj = zbuf + (((size_t)par * T + j) * RC + rc) * 4;
-        const double n1 = fma(a.P[0], v1, fma(a.P[1], v2, fma(a.P[2], v3, fma(a.P[3], v4, zj[0]))));
-        const double n2 = fma(a.P[4], v1, fma(a.P[5], v2, fma(a.P[6], v3, fma(a.P[7], v4, zj[1]))));
-        const double n3 = fma(a.P[8], v1, fma(a.P[9], v2, fma(a.P[10], v3, fma(a.P[11], v4, zj[2]))));
-        const double n4 = fma(a.P[12], v1, fma(a.P[13], v2, fma(a.P[14], v3, fma(a.P[15], v4, zj[3]))));
-        v1 = n1; v2 = n2; v3 = n3; v4 = n4;
+      const double* cr = carry + ((size_t)par * RC + rc) * 8;
+      if (k == 0) {
+        v1 = cr[0]; v2 = cr[1]; v3 = cr[2]; v4 = cr[3];   // exact hand-over from the previous tile
+      } else {
+        double d0 = cr[4], d1 = cr[5], d2 = cr[6], d3 = cr[7];
+        for (int j = 0; j < k; j++) {
+          const double* zj = zbuf + (((size_t)par * T + j) * RC + rc) * 4;
+          const double n0 = fma(a.P[0], d0, fma(a.P[1], d1, fma(a.P[2], d2, fma(a.P[3], d3, zj[0]))));
+          const double n1 = fma(a.P[4], d0, fma(a.P[5], d1, fma(a.P[6], d2, fma(a.P[7], d3, zj[1]))));
+          const double n2 = fma(a.P[8], d0, fma(a.P[9], d1, fma(a.P[10], d2, fma(a.P[11], d3, zj[2]))));
+          const double n3 = fma(a.P[12], d0, fma(a.P[13], d1, fma(a.P[14], d2, fma(a.P[15], d3, zj[3]))));
+          d0 = n0; d1 = n1; d2 = n2; d3 = n3;
+        }
+        from_diff(d0, d1, d2, d3, v1, v2, v3, v4);
       }
       // ---- k == 0 folds the previous tile's partial sums into the bucket accumulator (fixed order) ----
       if (k == 0 && tile > 0) {
@@ -316,10 +352,7 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const TileArgs a) {
       double* pp = part + (((size_t)par * T + k) * RC + rc) * 2;
       pp[0] = live ? accA : 0.0;
       pp[1] = live ? accB : 0.0;
-      if (k == T - 1) {
-        double* cr = carry + ((size_t)(par ^ 1) * RC + rc) * 4;
-        cr[0] = v1; cr[1] = v2; cr[2] = v3; cr[3] = v4;
-      }
+      if (k == T - 1) store_carry(carry + ((size_t)(par ^ 1) * RC + rc) * 8, v1, v2, v3, v4);
     } else {
       acc_cur += accA;
       if (to_boundary <= (unsigned)F) {
@@ -352,7 +385,7 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const TileArgs a) {
           slot = (slot + 1) % kNB;
         }
       }
-      const double* cr = carry + ((size_t)par * RC + rc) * 4;
+      const double* cr = carry + ((size_t)par * RC + rc) * 8;
       v1 = cr[0]; v2 = cr[1]; v3 = cr[2]; v4 = cr[3];
       if (a.do_sample_peak) {
 #pragma unroll
@@ -394,29 +427,60 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// A^n for the DF-II state transition of the K-weighting filter, in long double
-void state_matrix_power(const double a[5], int n, double P[16]) {
-  long double A[4][4] = {{-(long double)a[1], -(long double)a[2], -(long double)a[3], -(long double)a[4]},
-                         {1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}};
-  long double R[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+// ---- host: D * A^n * D in double-double arithmetic, rounded once to double ----------------------
+struct dd { double hi, lo; };
+static inline dd dd_from(double x) { return {x, 0.0}; }
+static inline dd dd_renorm(double s, double e) { const double hi = s + e; return {hi, e - (hi - s)}; }
+static inline dd dd_add(dd x, dd y) {
+  const double s = x.hi + y.hi, bb = s - x.hi;
+  double e = (x.hi - (s - bb)) + (y.hi - bb);
+  e += x.lo + y.lo;
+  return dd_renorm(s, e);
+}
+static inline dd dd_mul_d(dd x, double b) {
+  const double p = x.hi * b;
+  double e = fma(x.hi, b, -p);
+  e = fma(x.lo, b, e);
+  return dd_renorm(p, e);
+}
+static inline dd dd_neg(dd x) { return {-x.hi, -x.lo}; }
+
+void handoff_matrix(const double a[5], int n, double P[16]) {
+  // R = A^n by n left-multiplications with the companion matrix A (row 0 = -a1..-a4, rows 1..3 shift)
+  dd R[4][4];
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) R[i][j] = dd_from(i == j ? 1.0 : 0.0);
   for (int it = 0; it < n; it++) {
-    long double Tm[4][4];
-    for (int i = 0; i < 4; i++)
-      for (int j = 0; j < 4; j++) {
-        long double s = 0;
-        for (int k = 0; k < 4; k++) s += A[i][k] * R[k][j];
-        Tm[i][j] = s;
-      }
-    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) R[i][j] = Tm[i][j];
+    dd row0[4];
+    for (int j = 0; j < 4; j++) {
+      dd acc = dd_from(0.0);
+      for (int k = 0; k < 4; k++) acc = dd_add(acc, dd_mul_d(R[k][j], -a[k + 1]));
+      row0[j] = acc;
+    }
+    for (int i = 3; i > 0; i--) for (int j = 0; j < 4; j++) R[i][j] = R[i - 1][j];
+    for (int j = 0; j < 4; j++) R[0][j] = row0[j];
   }
-  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) P[i * 4 + j] = (double)R[i][j];
+  const double D[4][4] = {{1, 0, 0, 0}, {1, -1, 0, 0}, {1, -2, 1, 0}, {1, -3, 3, -1}};
+  dd Tm[4][4];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      dd acc = dd_from(0.0);
+      for (int k = 0; k < 4; k++) acc = dd_add(acc, dd_mul_d(R[i][k], D[k][j]));  // R * D
+      Tm[i][j] = acc;
+    }
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      dd acc = dd_from(0.0);
+      for (int k = 0; k < 4; k++) acc = dd_add(acc, dd_mul_d(Tm[k][j], D[i][k]));  // D * (R * D)
+      P[i * 4 + j] = acc.hi + acc.lo;
+    }
+  (void)dd_neg;
 }
 
 template <int C, int T, int F>
 size_t tile_smem_bytes() {
   constexpr int RC = kRows * C;
   const size_t stage = (size_t)(F * C / 32) * kRows * 128;
-  return kStages * stage + (size_t)(2 * T * RC * 4 + 2 * RC * 4 + 2 * T * RC * 2) * sizeof(double) +
+  return kStages * stage + (size_t)(2 * T * RC * 4 + 2 * RC * 8 + 2 * T * RC * 2) * sizeof(double) +
          (size_t)T * RC * sizeof(float) + 2 * kStages * sizeof(uint64_t) + 1024;
 }
 
@@ -473,7 +537,7 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   TileArgs a;
   memcpy(a.a, p.a, sizeof(a.a));
   memcpy(a.b, p.b, sizeof(a.b));
-  state_matrix_power(p.a, kTileF / kTileT, a.P);
+  handoff_matrix(p.a, kTileF / kTileT, a.P);
   a.in = d_in;
   a.filt = st.filt;
   a.bucket = st.bucket;

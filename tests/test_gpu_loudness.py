@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 
 LU_TOL = 1e-4
 TP_RTOL = 2e-6
+TILE_LU_TOL = 2e-9  # time-segmented kernel vs the serial recursion (tolerance of the path is LU_TOL = 1e-4)
 
 
 def close_lu(a, b, tol=LU_TOL):
@@ -202,7 +203,7 @@ def test_modes(ssb, oracle, cuda):
     ob = oracle.Batch(n, ch, rate, oracle.MODE_LOUDNESS)
     ob.add_frames(x)
     want = ob.query()
-    assert close_lu(b.loudness_global(), want["global"]) and close_lu(b.loudness_shortterm(), want["shortterm"], 1e-9)
+    assert close_lu(b.loudness_global(), want["global"]) and close_lu(b.loudness_shortterm(), want["shortterm"], TILE_LU_TOL)
     for q in (b.true_peak, b.sample_peak):
         with pytest.raises(ssb.SsbError) as e:
             q()
@@ -257,11 +258,11 @@ def test_cfg2_full_size_properties(ssb, oracle, cuda):
         ob.add_frames(np.ascontiguousarray(x[sub]))
     want = ob.query()
     m1, m2 = b.loudness_momentary(), b2.loudness_momentary()
-    assert close_lu(m1[sub], want["momentary"], 1e-9)
-    assert close_lu(b.loudness_shortterm()[sub], want["shortterm"], 1e-9)
+    assert close_lu(m1[sub], want["momentary"], TILE_LU_TOL)
+    assert close_lu(b.loudness_shortterm()[sub], want["shortterm"], TILE_LU_TOL)
     assert close_lu(b.loudness_global()[sub], want["global"])
     assert close_lu(b.loudness_range()[sub], want["range"])
-    assert np.allclose(m2 - m1, 20 * np.log10(2.0), rtol=0, atol=1e-9)   # exact doubling -> +6.0206 LU
+    assert np.allclose(m2 - m1, 20 * np.log10(2.0), rtol=0, atol=1e-12)   # doubling is exact in binary -> +6.0206 LU
     assert np.all(np.isfinite(b.loudness_global()))
 
 
@@ -291,9 +292,13 @@ def test_tile_kernel_matches_generic_and_oracle(ssb, oracle, cuda, channels, fra
         assert close_lu(h.loudness_range(), want["range"])
         assert np.array_equal(h.sample_peak(), np.abs(x).max(axis=1).astype(np.float64))
     if (frames * 5) % 4800 == 0:
-        for h in (fast, slow):
-            assert close_lu(h.loudness_momentary(), want["momentary"], 1e-9)
-            assert close_lu(h.loudness_shortterm(), want["shortterm"], 1e-9)
+        # serial kernel: same operation order as the oracle up to FMA contraction.  Time-segmented kernel:
+        # the segment hand-off (s_k = P s_{k-1} + z) re-rounds the state once per segment; measured ~1e-9 LU.
+        d = np.abs(fast.loudness_momentary() - want["momentary"])
+        print("tile kernel max |dLUFS| vs oracle:", d[np.isfinite(d)].max())
+        for h, tol in ((slow, 1e-9), (fast, TILE_LU_TOL)):
+            assert close_lu(h.loudness_momentary(), want["momentary"], tol)
+            assert close_lu(h.loudness_shortterm(), want["shortterm"], tol)
     for s in (0, 150, n - 1):
         assert np.array_equal(fast.histograms(s)[0], slow.histograms(s)[0])
         assert np.array_equal(fast.histograms(s)[0], ob._per_stream_hist(s)[0])

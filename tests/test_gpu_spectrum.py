@@ -5,7 +5,8 @@ Tolerances
   waveform, mid/side bit-exact (indices AND values; north_star: "bit-exact min-max decimation indices")
   FFT magnitude     |dmag| <= 1e-5 * max|X| over all kept bins (north_star's 1e-5 relative, defined against the
                     window's peak bin because bins near the f32 noise floor are rounding noise in BOTH
-                    implementations), and |d dB| <= 1e-4 dB for every bin within 60 dB of the peak.
+                    implementations: f32 FFT round-off is ~1e-7 * max|X| in EVERY bin, i.e. already 1e-4
+                    relative at -60 dB), and |d dB| <= 1e-4 dB for every bin within 20 dB of the peak.
 """
 import os
 
@@ -24,7 +25,7 @@ def assert_db_close(got_db, want_db):
     mg, mw = 10 ** (got_db / 20), 10 ** (want_db / 20)
     peak = mw.max()
     assert np.max(np.abs(mg - mw)) <= 1e-5 * peak
-    near = want_db >= want_db.max() - 60.0
+    near = want_db >= want_db.max() - 20.0
     assert np.max(np.abs(got_db[near] - want_db[near])) <= 1e-4
 
 
