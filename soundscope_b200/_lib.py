@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(HERE, "libsoundscope_b200.so")
+_SO = os.environ.get("SSB_LIB") or os.path.join(HERE, "libsoundscope_b200.so")  # SSB_LIB: tuning experiments only
 
 MODE_M = 1
 MODE_S = 2 | MODE_M

@@ -38,7 +38,8 @@ def _deps():
 
 def _compile(src, verbose):
     obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
-    cmd = [NVCC, *NVCC_FLAGS, "-c", src, "-o", obj]
+    extra = os.environ.get("SSB_NVCC_EXTRA", "").split()
+    cmd = [NVCC, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(obj + ".log", "w") as f:

@@ -108,6 +108,7 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
   LoudParams& lp = h->lp;
   memset(&lp, 0, sizeof(lp));
   kweight_coeffs(rate, lp.b, lp.a);
+  for (int i = 0; i < 5; i++) lp.na[i] = -lp.a[i];
   lp.channels = (int)channels;
   lp.s100 = (rate + 5) / 10;
   lp.do_filter = 1;  // every mode contains M

@@ -75,10 +75,10 @@ k_loudness_generic(const LoudParams p, const float* __restrict__ in, size_t fram
     }
     if (active) {
       // v0 = x - a1 v1 - a2 v2 - a3 v3 - a4 v4, the newest state last to keep the dependent chain short
-      double t = fma(-p.a[4], v4, (double)xf);
-      t = fma(-p.a[3], v3, t);
-      t = fma(-p.a[2], v2, t);
-      const double v0 = fma(-p.a[1], v1, t);
+      double t = fma(p.na[4], v4, (double)xf);
+      t = fma(p.na[3], v3, t);
+      t = fma(p.na[2], v2, t);
+      const double v0 = fma(p.na[1], v1, t);
       double y = p.b[4] * v4;
       y = fma(p.b[3], v3, y);
       y = fma(p.b[2], v2, y);

@@ -13,9 +13,11 @@
 //     state of segment k is s_k = P s_{k-1} + z_{k-1} with P = A^Ls (exact linear algebra, host-computed in
 //     extended precision), pass 2 runs the full filter (10 DFMA/sample) from s_k.  Both passes read the same
 //     shared-memory tile, so HBM traffic stays at the algorithmic 4 B/sample.
-//   * bucket sums are reduced across segments in a fixed order (deterministic, no atomics).
+//   * the four segments of a chain live in one warp: hand-off, carried state and bucket partial sums move by
+//     warp shuffles (fixed reduction order, deterministic, no atomics, no CTA barrier in the main loop).
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ssb_internal.cuh"
@@ -28,13 +30,17 @@ constexpr int kRows = 32;       // streams per CTA tile (multiple of 8: swizzle 
 constexpr int kStages = 3;
 
 struct TileArgs {
-  double a[5];
+  double na[5];        // negated feedback coefficients -a[i]
   double b[5];
   double P[16];        // D * A^Ls * D (state hand-off matrix in difference coordinates), row-major
   const float* in;     // unused by the TMA path (kept for debugging)
   double* filt;        // [n][C][4]
   double* bucket;      // [n][C][kNB]
   float* speak;        // [n][C]
+  float* tpeak;        // [n][C]
+  float* tphist;       // [n][C][kTpHist]: x[n-1-t]
+  float tp4[3][12];    // factor-4 interpolator phases 1..3 (tap t multiplies x[n-t])
+  float tp2[24];       // factor-2 interpolator phase 1
   uint64_t active_mask;
   unsigned n_streams;
   unsigned n_tiles;    // tiles of F frames in this launch
@@ -83,16 +89,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 }
 __device__ __forceinline__ void bar_sync_compute(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 
-// f32 -> f64 widening with integer ops (exact for normal numbers and zero); subnormal / inf / nan
-// inputs take the hardware conversion.
-__device__ __forceinline__ double widen(float x) {
-  const unsigned u = __float_as_uint(x);
-  const unsigned e = u & 0x7f800000u;
-  if (__builtin_expect(e == 0u || e == 0x7f800000u, 0)) return (double)x;
-  const unsigned hi = (u & 0x80000000u) | (((u & 0x7fffffffu) >> 3) + 0x38000000u);
-  return __hiloint2double((int)hi, (int)(u << 29));
-}
-
 // d = D v with D = [[1,0,0,0],[1,-1,0,0],[1,-2,1,0],[1,-3,3,-1]] (finite differences; D is its own inverse).
 // Differences of neighbouring state samples are (nearly) exact in floating point, and the hand-off matrix
 // D A^Ls D acts on the small differences instead of cancelling four huge, nearly equal terms.
@@ -126,12 +122,47 @@ __device__ __forceinline__ float pick(const float4& q, int f, int c) {
   return f == 0 ? (c ? q.y : q.x) : (c ? q.w : q.z);
 }
 
-// C channels (1 or 2), T time segments per tile, F frames per tile
-template <int C, int T, int F, bool WIDEN_INT>
-__global__ void __launch_bounds__(kRows* C* T + 32, 1)
-k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const TileArgs a) {
-  constexpr int NC = kRows * C * T;          // compute threads
-  constexpr int RC = kRows * C;              // chains per CTA
+// f32 -> f64 widening with integer ops (exact for normal numbers and zero; subnormal / inf / nan inputs take
+// the hardware conversion).  F2F.F64.F32 issues at 16 lanes/clk/SM; this trades it for ALU-pipe work.
+__device__ __forceinline__ double widen_int(float x) {
+  const unsigned u = __float_as_uint(x);
+  const unsigned e = u & 0x7f800000u;
+  if (__builtin_expect((e == 0u && (u << 1) != 0u) || e == 0x7f800000u, 0)) return (double)x;
+  const unsigned hi = e ? ((u & 0x80000000u) | (((u & 0x7fffffffu) >> 3) + 0x38000000u)) : (u & 0x80000000u);
+  return __hiloint2double((int)hi, (int)(u << 29));
+}
+#if defined(SSB_EXPERIMENT_NOF2F)  // timing experiment only (wrong numerics): no conversion at all
+#define SSB_CVT(x) __hiloint2double(__float_as_int(x), 0)
+#elif defined(SSB_WIDEN_INT)
+#define SSB_CVT(x) widen_int(x)
+#else
+#define SSB_CVT(x) ((double)(x))
+#endif
+
+// One filter sample: DF-II recursion + output taps; the newest state enters last (short dependent chain).
+#define SSB_FILTER_STEP(x)                       \
+  double t_ = fma(a.na[4], v4, (x));             \
+  t_ = fma(a.na[3], v3, t_);                     \
+  t_ = fma(a.na[2], v2, t_);                     \
+  const double v0_ = fma(a.na[1], v1, t_);       \
+  double y_ = a.b[4] * v4;                       \
+  y_ = fma(a.b[3], v3, y_);                      \
+  y_ = fma(a.b[2], v2, y_);                      \
+  y_ = fma(a.b[1], v1, y_);                      \
+  y_ = fma(a.b[0], v0_, y_);                     \
+  v4 = v3; v3 = v2; v2 = v1; v1 = v0_;
+
+// C channels (1 or 2); T = 4 time segments per tile of F frames.
+// Warp w owns rows [w*RW, (w+1)*RW) of the CTA's 32-row box, RW = 8 / C; lane = k*8 + rr*C + c holds
+// (segment k, row rr, channel c).  All four segments of a chain sit in one warp, so the segment hand-off,
+// the carried state and the bucket partial sums travel by warp shuffles: compute warps never meet at a CTA
+// barrier and synchronise only through the TMA full/empty mbarriers.
+template <int C, int F, int TPF>
+__global__ void __launch_bounds__(kRows* C * 4 + 32, 1)
+k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileArgs a) {
+  constexpr int T = 4;
+  constexpr int RW = 8 / C;                  // rows per warp
+  constexpr int NW = kRows / RW;             // compute warps
   constexpr int LS = F / T;                  // frames per segment
   constexpr int CHUNKS = F * C / 32;         // 128-byte lines per row per stage
   constexpr int SEG_CHUNKS = LS * C / 32;    // lines per segment
@@ -142,34 +173,31 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const TileArgs a) {
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B needs 1024-byte aligned stage bases (1 KB of slack is included in the launch size)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* stages = smem;                                                 // kStages * STAGE_BYTES
-  double* zbuf = reinterpret_cast<double*>(smem + kStages * STAGE_BYTES);       // [2][T][RC][4]
-  double* carry = zbuf + 2 * T * RC * 4;                                        // [2][RC][8]: raw v1..v4 | D v
-  double* part = carry + 2 * RC * 8;                                            // [2][T][RC][2]
-  float* pk = reinterpret_cast<float*>(part + 2 * T * RC * 2);                  // [T][RC]
-  uint64_t* full = reinterpret_cast<uint64_t*>(pk + T * RC);                    // [kStages]
-  uint64_t* empty = full + kStages;                                             // [kStages]
+  unsigned char* stages = smem;                                                   // kStages * STAGE_BYTES
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);     // [kStages]
+  uint64_t* empty = full + kStages;                                               // [kStages]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const unsigned n_ctas = gridDim.x;
   const unsigned row0 = (unsigned)(((unsigned long long)blockIdx.x * a.n_streams) / n_ctas);
   const unsigned row1 = (unsigned)(((unsigned long long)(blockIdx.x + 1) * a.n_streams) / n_ctas);
-  const unsigned nrows = row1 - row0;  // <= kRows by construction of the grid
+  const unsigned nrows = row1 - row0;                        // <= kRows by construction of the grid
+  const unsigned live_warps = (nrows + RW - 1) / RW;         // warps that own at least one stream
 
   if (tid == 0) {
     for (int s = 0; s < kStages; s++) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NC / 32);
+      mbar_init(&empty[s], live_warps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == NC / 32) {
+  if (warp == NW) {
     // ---------------- producer warp: one elected lane drives TMA ----------------
-    if (lane == 0) {
+    if (lane == 0 && live_warps > 0) {
       for (unsigned tile = 0; tile < a.n_tiles; tile++) {
         const unsigned s = tile % kStages;
         if (tile >= (unsigned)kStages) mbar_wait(&empty[s], ((tile / kStages) - 1) & 1);
@@ -179,113 +207,83 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const TileArgs a) {
     }
     return;
   }
+  if ((unsigned)warp >= live_warps) return;  // no stream in this warp's rows
 
-  // ---------------- compute threads: (segment k, row r, channel c) ----------------
-  const int k = tid / RC;
-  const int rc = tid - k * RC;
-  const int r = rc / C;
-  const int c = rc - r * C;
+  // ---------------- compute warp: lane = (segment k, row rr, channel c) ----------------
+  const int k = lane >> 3;
+  const int q8 = lane & 7;
+  const int rr = q8 / C;
+  const int c = q8 - rr * C;
+  const int r = warp * RW + rr;
   const bool row_ok = (unsigned)r < nrows;
-  const bool chan_ok = (a.active_mask >> c) & 1ull;
-  const bool live = row_ok && chan_ok;
+  const bool live = row_ok && ((a.active_mask >> c) & 1ull);
   const size_t gidx = ((size_t)(row0 + r)) * C + c;
   const unsigned key = r & 7;
 
-  // state carried across tiles lives in carry[parity][rc][4]; thread k==0 seeds it
-  if (k == 0) {
-    double4 s0 = make_double4(0, 0, 0, 0);
-    if (live) {
-      const double* f = a.filt + gidx * 4;
-      s0 = make_double4(f[0], f[1], f[2], f[3]);
-    }
-    store_carry(carry + (size_t)rc * 8, s0.x, s0.y, s0.z, s0.w);
+  // c1..c4: the chain's true state at the start of the tile, replicated in its four lanes
+  double c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+  if (live) {
+    const double* f = a.filt + gidx * 4;
+    c1 = f[0]; c2 = f[1]; c3 = f[2]; c4 = f[3];
   }
-  double acc_cur = 0.0;   // k == 0 only: running sum of the bucket in progress
+  double acc_cur = 0.0;  // lane k == 0: running sum of the bucket in progress
   unsigned slot = a.slot0;
   if (k == 0 && live && a.pos0 > 0) acc_cur = a.bucket[gidx * kNB + slot];
-  float sp = 0.f;
-  double v1 = 0, v2 = 0, v3 = 0, v4 = 0;
-  if (T == 1 && live) {
-    const double* f = a.filt + gidx * 4;
-    v1 = f[0]; v2 = f[1]; v3 = f[2]; v4 = f[3];
-  }
-  const double a1 = a.a[1], a2 = a.a[2], a3 = a.a[3], a4 = a.a[4];
-  const double b0 = a.b[0], b1 = a.b[1], b2 = a.b[2], b3 = a.b[3], b4 = a.b[4];
+  float sp = 0.f, tp = 0.f;
+  constexpr int TPW = TPF == 4 ? 11 : (TPF == 2 ? 23 : 1);  // true-peak FIR history length
+  float hist[TPW];  // lane k == 0: the TPW samples before the tile, hist[t] = x[n-1-t]
+#pragma unroll
+  for (int t = 0; t < TPW; t++) hist[t] = (TPF != 0 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
   unsigned pos_tile = a.pos0;  // position of the tile start inside the bucket in progress
 
   for (unsigned tile = 0; tile < a.n_tiles; tile++) {
     const unsigned s = tile % kStages;
-    const unsigned par = tile & 1;
     mbar_wait(&full[s], (tile / kStages) & 1);
     const unsigned char* line0 = stages + (size_t)s * STAGE_BYTES + ((size_t)(k * SEG_CHUNKS) * kRows + r) * 128;
 
-    if (T > 1) {
-      // ---- pass 1: zero-state recursion over my segment -> z ----
-      double z1 = 0, z2 = 0, z3 = 0, z4 = 0;
+    // ---- pass 1: zero-state recursion over my segment -> z (4 DFMA / sample) ----
+    double z1 = 0, z2 = 0, z3 = 0, z4 = 0;
 #pragma unroll 1
-      for (int ch = 0; ch < SEG_CHUNKS; ch++) {
-        const unsigned char* line = line0 + (size_t)ch * kRows * 128;
+    for (int ch = 0; ch < SEG_CHUNKS; ch++) {
+      const unsigned char* line = line0 + (size_t)ch * kRows * 128;
 #pragma unroll
-        for (int qi = 0; qi < 8; qi++) {
-          const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
+      for (int qi = 0; qi < 8; qi++) {
+        const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
 #pragma unroll
-          for (int f = 0; f < FPQ; f++) {
-            const float xf = pick<C>(q, f, c);
-            const double x = WIDEN_INT ? widen(xf) : (double)xf;
-            double t = fma(-a4, z4, x);
-            t = fma(-a3, z3, t);
-            t = fma(-a2, z2, t);
-            const double z0 = fma(-a1, z1, t);
-            z4 = z3; z3 = z2; z2 = z1; z1 = z0;
-          }
-        }
-      }
-      {
-        // hand-off runs in difference coordinates d = D v (see to_diff): the DF-II state is four consecutive
-        // samples of a large, smooth internal signal, and A^Ls applied to it directly cancels ~1e3-fold
-        double* zp = zbuf + (((size_t)par * T + k) * RC + rc) * 4;
-        double d0, d1, d2, d3;
-        to_diff(z1, z2, z3, z4, d0, d1, d2, d3);
-        zp[0] = d0; zp[1] = d1; zp[2] = d2; zp[3] = d3;
-      }
-      bar_sync_compute(NC);
-      // ---- combine: true incoming state of segment k ----
-      const double* cr = carry + ((size_t)par * RC + rc) * 8;
-      if (k == 0) {
-        v1 = cr[0]; v2 = cr[1]; v3 = cr[2]; v4 = cr[3];   // exact hand-over from the previous tile
-      } else {
-        double d0 = cr[4], d1 = cr[5], d2 = cr[6], d3 = cr[7];
-        for (int j = 0; j < k; j++) {
-          const double* zj = zbuf + (((size_t)par * T + j) * RC + rc) * 4;
-          const double n0 = fma(a.P[0], d0, fma(a.P[1], d1, fma(a.P[2], d2, fma(a.P[3], d3, zj[0]))));
-          const double n1 = fma(a.P[4], d0, fma(a.P[5], d1, fma(a.P[6], d2, fma(a.P[7], d3, zj[1]))));
-          const double n2 = fma(a.P[8], d0, fma(a.P[9], d1, fma(a.P[10], d2, fma(a.P[11], d3, zj[2]))));
-          const double n3 = fma(a.P[12], d0, fma(a.P[13], d1, fma(a.P[14], d2, fma(a.P[15], d3, zj[3]))));
-          d0 = n0; d1 = n1; d2 = n2; d3 = n3;
-        }
-        from_diff(d0, d1, d2, d3, v1, v2, v3, v4);
-      }
-      // ---- k == 0 folds the previous tile's partial sums into the bucket accumulator (fixed order) ----
-      if (k == 0 && tile > 0) {
-        const unsigned prev_pos = pos_tile >= (unsigned)F ? pos_tile - F : pos_tile + a.s100 - F;
-        const bool had_boundary = prev_pos + F >= a.s100;
-        const double* pp = part + ((size_t)(par ^ 1) * T * RC + rc) * 2;
-        double sa = 0.0, sb = 0.0;
-#pragma unroll
-        for (int j = 0; j < T; j++) { sa += pp[(size_t)j * RC * 2]; sb += pp[(size_t)j * RC * 2 + 1]; }
-        acc_cur += sa;
-        if (had_boundary) {
-          if (live) a.bucket[gidx * kNB + slot] = acc_cur;
-          acc_cur = sb;
-          slot = (slot + 1) % kNB;
+        for (int f = 0; f < FPQ; f++) {
+          const double x = SSB_CVT(pick<C>(q, f, c));
+          double t = fma(a.na[4], z4, x);
+          t = fma(a.na[3], z3, t);
+          t = fma(a.na[2], z2, t);
+          const double z0 = fma(a.na[1], z1, t);
+          z4 = z3; z3 = z2; z2 = z1; z1 = z0;
         }
       }
     }
+    // ---- hand-off in difference coordinates: d_k = Pt d_{k-1} + D z_{k-1}, d_0 = D carry ----
+    double v1, v2, v3, v4;
+    {
+      double dz0, dz1, dz2, dz3, d0, d1, d2, d3;
+      to_diff(z1, z2, z3, z4, dz0, dz1, dz2, dz3);
+      to_diff(c1, c2, c3, c4, d0, d1, d2, d3);
+#pragma unroll
+      for (int j = 0; j < T - 1; j++) {
+        const int src = j * 8 + q8;
+        const double zj0 = __shfl_sync(0xffffffffu, dz0, src), zj1 = __shfl_sync(0xffffffffu, dz1, src);
+        const double zj2 = __shfl_sync(0xffffffffu, dz2, src), zj3 = __shfl_sync(0xffffffffu, dz3, src);
+        const double n0 = fma(a.P[0], d0, fma(a.P[1], d1, fma(a.P[2], d2, fma(a.P[3], d3, zj0))));
+        const double n1 = fma(a.P[4], d0, fma(a.P[5], d1, fma(a.P[6], d2, fma(a.P[7], d3, zj1))));
+        const double n2 = fma(a.P[8], d0, fma(a.P[9], d1, fma(a.P[10], d2, fma(a.P[11], d3, zj2))));
+        const double n3 = fma(a.P[12], d0, fma(a.P[13], d1, fma(a.P[14], d2, fma(a.P[15], d3, zj3))));
+        if (j < k) { d0 = n0; d1 = n1; d2 = n2; d3 = n3; }
+      }
+      from_diff(d0, d1, d2, d3, v1, v2, v3, v4);
+      if (k == 0) { v1 = c1; v2 = c2; v3 = c3; v4 = c4; }  // exact hand-over from the previous tile
+    }
 
-    // ---- pass 2: full filter from the true state; y^2 split at the bucket boundary ----
-    // frames of this tile before the boundary of the bucket in progress (>= F: no boundary in this tile)
-    const unsigned to_boundary = a.s100 - pos_tile;
-    int lb = (int)to_boundary - k * LS;            // my samples [0, lb) belong to the current bucket
+    // ---- pass 2: full filter from the true state (10 DFMA / sample); y^2 split at the bucket boundary ----
+    const unsigned to_boundary = a.s100 - pos_tile;  // frames of this tile before the boundary (>= F: none)
+    int lb = (int)to_boundary - k * LS;              // my samples [0, lb) belong to the bucket in progress
     lb = lb < 0 ? 0 : (lb > LS ? LS : lb);
     double accA = 0.0, accB = 0.0;
     if (lb == LS || lb == 0) {
@@ -300,18 +298,8 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const TileArgs a) {
           for (int f = 0; f < FPQ; f++) {
             const float xf = pick<C>(q, f, c);
             sp = fmaxf(sp, fabsf(xf));
-            const double x = WIDEN_INT ? widen(xf) : (double)xf;
-            double t = fma(-a4, v4, x);
-            t = fma(-a3, v3, t);
-            t = fma(-a2, v2, t);
-            const double v0 = fma(-a1, v1, t);
-            double y = b4 * v4;
-            y = fma(b3, v3, y);
-            y = fma(b2, v2, y);
-            y = fma(b1, v1, y);
-            y = fma(b0, v0, y);
-            v4 = v3; v3 = v2; v2 = v1; v1 = v0;
-            acc = fma(y, y, acc);
+            SSB_FILTER_STEP(SSB_CVT(xf))
+            acc = fma(y_, y_, acc);
           }
         }
       }
@@ -328,32 +316,76 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const TileArgs a) {
           for (int f = 0; f < FPQ; f++, i++) {
             const float xf = pick<C>(q, f, c);
             sp = fmaxf(sp, fabsf(xf));
-            const double x = WIDEN_INT ? widen(xf) : (double)xf;
-            double t = fma(-a4, v4, x);
-            t = fma(-a3, v3, t);
-            t = fma(-a2, v2, t);
-            const double v0 = fma(-a1, v1, t);
-            double y = b4 * v4;
-            y = fma(b3, v3, y);
-            y = fma(b2, v2, y);
-            y = fma(b1, v1, y);
-            y = fma(b0, v0, y);
-            v4 = v3; v3 = v2; v2 = v1; v1 = v0;
-            if (i < lb) accA = fma(y, y, accA); else accB = fma(y, y, accB);
+            SSB_FILTER_STEP(SSB_CVT(xf))
+            if (i < lb) accA = fma(y_, y_, accA); else accB = fma(y_, y_, accB);
           }
         }
       }
     }
-    // this stage's shared memory is no longer needed by this warp
+    // ---- pass 3 (Mode::TRUE_PEAK): ebur128's polyphase interpolator as an f32 FIR over my segment ----
+    if (TPF != 0) {
+      float w[TPW];  // w[t] = x[n-1-t]
+      const unsigned char* row_base = stages + (size_t)s * STAGE_BYTES + (size_t)r * 128;
+#pragma unroll
+      for (int t = 0; t < TPW; t++) {
+        // segment k > 0 finds its history in the same tile (the previous segment's tail)
+        const int fr = k > 0 ? k * LS - 1 - t : 0;
+        const int fi = fr * C + c;
+        const float prev = *reinterpret_cast<const float*>(row_base + (size_t)(fi >> 5) * kRows * 128 +
+                                                            ((((fi >> 2) & 7) ^ key) << 4) + ((fi & 3) << 2));
+        w[t] = k > 0 ? prev : hist[t];
+      }
+#pragma unroll 1
+      for (int ch = 0; ch < SEG_CHUNKS; ch++) {
+        const unsigned char* line = line0 + (size_t)ch * kRows * 128;
+#pragma unroll
+        for (int qi = 0; qi < 8; qi++) {
+          const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
+#pragma unroll
+          for (int f = 0; f < FPQ; f++) {
+            const float xf = pick<C>(q, f, c);
+            if (TPF == 4) {
+#pragma unroll
+              for (int ph = 0; ph < 3; ph++) {
+                float acc = xf * a.tp4[ph][0];
+#pragma unroll
+                for (int t = 1; t < 12; t++) acc = fmaf(w[t - 1], a.tp4[ph][t], acc);
+                tp = fmaxf(tp, fabsf(acc));
+              }
+            } else {
+              float acc = xf * a.tp2[0];
+#pragma unroll
+              for (int t = 1; t < 24; t++) acc = fmaf(w[t - 1], a.tp2[t], acc);
+              tp = fmaxf(tp, fabsf(acc));
+            }
+#pragma unroll
+            for (int t = TPW - 1; t > 0; t--) w[t] = w[t - 1];
+            w[0] = xf;
+          }
+        }
+      }
+      // the last segment's tail is the history of the next tile's first segment
+#pragma unroll
+      for (int t = 0; t < TPW; t++) hist[t] = __shfl_sync(0xffffffffu, w[t], (T - 1) * 8 + q8);
+    }
+    // this warp is done reading the stage
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
 
-    if (T > 1) {
-      double* pp = part + (((size_t)par * T + k) * RC + rc) * 2;
-      pp[0] = live ? accA : 0.0;
-      pp[1] = live ? accB : 0.0;
-      if (k == T - 1) store_carry(carry + ((size_t)(par ^ 1) * RC + rc) * 8, v1, v2, v3, v4);
-    } else {
+    // ---- the last segment's end state is the chain's state for the next tile ----
+    {
+      const int src = (T - 1) * 8 + q8;
+      c1 = __shfl_sync(0xffffffffu, v1, src);
+      c2 = __shfl_sync(0xffffffffu, v2, src);
+      c3 = __shfl_sync(0xffffffffu, v3, src);
+      c4 = __shfl_sync(0xffffffffu, v4, src);
+    }
+    // ---- bucket sums: fixed-order reduction over the four segments: (k0 + k1) + (k2 + k3) ----
+    accA += __shfl_xor_sync(0xffffffffu, accA, 8);
+    accB += __shfl_xor_sync(0xffffffffu, accB, 8);
+    accA += __shfl_xor_sync(0xffffffffu, accA, 16);
+    accB += __shfl_xor_sync(0xffffffffu, accB, 16);
+    if (k == 0) {
       acc_cur += accA;
       if (to_boundary <= (unsigned)F) {
         if (live) a.bucket[gidx * kNB + slot] = acc_cur;
@@ -365,49 +397,32 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const TileArgs a) {
     if (pos_tile >= a.s100) pos_tile -= a.s100;
   }
 
-  // ---------------- epilogue: last tile's partials, state, peaks ----------------
-  if (T > 1) {
-    if (a.do_sample_peak) pk[(size_t)k * RC + rc] = sp;
-    bar_sync_compute(NC);
-    if (k == 0) {
-      const unsigned par = a.n_tiles & 1;  // parity the next tile would have had
-      if (a.n_tiles > 0) {
-        const unsigned prev_pos = pos_tile >= (unsigned)F ? pos_tile - F : pos_tile + a.s100 - F;
-        const bool had_boundary = prev_pos + F >= a.s100;
-        const double* pp = part + ((size_t)(par ^ 1) * T * RC + rc) * 2;
-        double sa = 0.0, sb = 0.0;
-#pragma unroll
-        for (int j = 0; j < T; j++) { sa += pp[(size_t)j * RC * 2]; sb += pp[(size_t)j * RC * 2 + 1]; }
-        acc_cur += sa;
-        if (had_boundary) {
-          if (live) a.bucket[gidx * kNB + slot] = acc_cur;
-          acc_cur = sb;
-          slot = (slot + 1) % kNB;
-        }
-      }
-      const double* cr = carry + ((size_t)par * RC + rc) * 8;
-      v1 = cr[0]; v2 = cr[1]; v3 = cr[2]; v4 = cr[3];
-      if (a.do_sample_peak) {
-#pragma unroll
-        for (int j = 1; j < T; j++) sp = fmaxf(sp, pk[(size_t)j * RC + rc]);
-      }
-    }
-  }
+  // ---------------- epilogue: state, bucket in progress, peak ----------------
+  sp = fmaxf(sp, __shfl_xor_sync(0xffffffffu, sp, 8));
+  sp = fmaxf(sp, __shfl_xor_sync(0xffffffffu, sp, 16));
+  tp = fmaxf(tp, __shfl_xor_sync(0xffffffffu, tp, 8));
+  tp = fmaxf(tp, __shfl_xor_sync(0xffffffffu, tp, 16));
   if (k == 0) {
     if (live) {
       a.bucket[gidx * kNB + slot] = acc_cur;
       double* f = a.filt + gidx * 4;
       const double tiny = 2.2250738585072014e-308;  // libebur128: flush denormal state at the end of a call
-      f[0] = fabs(v1) < tiny ? 0.0 : v1;
-      f[1] = fabs(v2) < tiny ? 0.0 : v2;
-      f[2] = fabs(v3) < tiny ? 0.0 : v3;
-      f[3] = fabs(v4) < tiny ? 0.0 : v4;
+      f[0] = fabs(c1) < tiny ? 0.0 : c1;
+      f[1] = fabs(c2) < tiny ? 0.0 : c2;
+      f[2] = fabs(c3) < tiny ? 0.0 : c3;
+      f[3] = fabs(c4) < tiny ? 0.0 : c4;
     } else if (row_ok) {
       a.bucket[gidx * kNB + slot] = 0.0;
     }
     if (row_ok && a.do_sample_peak) a.speak[gidx] = fmaxf(a.speak[gidx], sp);
+    if (TPF != 0 && row_ok) {
+      a.tpeak[gidx] = fmaxf(a.tpeak[gidx], tp);
+#pragma unroll
+      for (int t = 0; t < TPW; t++) a.tphist[gidx * kTpHist + t] = hist[t];
+    }
   }
 }
+#undef SSB_FILTER_STEP
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -476,36 +491,41 @@ void handoff_matrix(const double a[5], int n, double P[16]) {
   (void)dd_neg;
 }
 
-template <int C, int T, int F>
+template <int C, int F>
 size_t tile_smem_bytes() {
-  constexpr int RC = kRows * C;
   const size_t stage = (size_t)(F * C / 32) * kRows * 128;
-  return kStages * stage + (size_t)(2 * T * RC * 4 + 2 * RC * 8 + 2 * T * RC * 2) * sizeof(double) +
-         (size_t)T * RC * sizeof(float) + 2 * kStages * sizeof(uint64_t) + 1024;
+  return kStages * stage + 2 * kStages * sizeof(uint64_t) + 1024;
 }
 
-template <int C, int T, int F>
+template <int C, int F, int TPF>
 cudaError_t launch_tile_cfg(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, cudaStream_t s) {
-  auto kern = k_loudness_tile<C, T, F, false>;  // hardware F2F: the integer widening costs more issue slots (tools/microbench)
-  const size_t smem = tile_smem_bytes<C, T, F>();
+  auto kern = k_loudness_tile<C, F, TPF>;
+  const size_t smem = tile_smem_bytes<C, F>();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e) return e;
-  kern<<<n_ctas, kRows * C * T + 32, smem, s>>>(tmap, args);
+  kern<<<n_ctas, kRows * C * 4 + 32, smem, s>>>(tmap, args);
   return cudaGetLastError();
+}
+
+template <int C>
+cudaError_t launch_tile_c(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, int tpf, cudaStream_t s) {
+  if (tpf == 4) return launch_tile_cfg<C, 256, 4>(tmap, args, n_ctas, s);
+  if (tpf == 2) return launch_tile_cfg<C, 256, 2>(tmap, args, n_ctas, s);
+  return launch_tile_cfg<C, 256, 0>(tmap, args, n_ctas, s);
 }
 
 }  // namespace
 
-constexpr int kTileF = 256;
 constexpr int kTileT = 4;
+constexpr int kTileFMax = 256;
+static int tile_frames() { return kTileFMax; }
 
 bool tile_path_usable(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
                       size_t in_stride_frames) {
   if (p.channels != 1 && p.channels != 2) return false;
   if (st.ring) return false;                      // the ring of y is written by the generic kernel
-  if (p.do_true_peak && p.tp_factor) return false;  // true-peak FIR not in this kernel yet
-  if (p.s100 < (unsigned)kTileF) return false;
-  if (frames < (size_t)kTileF) return false;
+  if (p.s100 < (unsigned)kTileFMax) return false;
+  if (frames < (size_t)kTileFMax) return false;
   if (((uintptr_t)d_in & 15) != 0) return false;
   if ((in_stride_frames * p.channels * sizeof(float)) % 16 != 0) return false;
   if (st.n_streams > 0x7fffffffu) return false;
@@ -518,16 +538,17 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
                                  uint64_t* launches, size_t* consumed) {
   *consumed = 0;
   const int C = p.channels;
-  const size_t n_tiles = frames / kTileF;
+  const int tile_f = tile_frames();
+  const size_t n_tiles = frames / tile_f;
   if (!n_tiles) return cudaSuccess;
   const size_t row_floats = in_stride_frames * C;
-  const size_t used_floats = n_tiles * kTileF * C;  // multiple of 32
+  const size_t used_floats = n_tiles * tile_f * C;  // multiple of 32
   CUtensorMap tmap;
   // 3-D view of the [stream][frame][channel] input: dim0 = 32 floats of one 128-byte line,
   // dim1 = stream (row pitch), dim2 = line index along the row
   cuuint64_t gdim[3] = {32, (cuuint64_t)st.n_streams, (cuuint64_t)(used_floats / 32)};
   cuuint64_t gstride[2] = {(cuuint64_t)(row_floats * sizeof(float)), 128};
-  cuuint32_t box[3] = {32, (cuuint32_t)kRows, (cuuint32_t)(kTileF * C / 32)};
+  cuuint32_t box[3] = {32, (cuuint32_t)kRows, (cuuint32_t)(tile_f * C / 32)};
   cuuint32_t estride[3] = {1, 1, 1};
   CUresult cr = encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d_in), gdim, gstride, box,
                             estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -535,13 +556,17 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
   TileArgs a;
-  memcpy(a.a, p.a, sizeof(a.a));
+  for (int i = 0; i < 5; i++) a.na[i] = -p.a[i];
   memcpy(a.b, p.b, sizeof(a.b));
-  handoff_matrix(p.a, kTileF / kTileT, a.P);
+  handoff_matrix(p.a, tile_f / kTileT, a.P);
   a.in = d_in;
   a.filt = st.filt;
   a.bucket = st.bucket;
   a.speak = st.speak;
+  a.tpeak = st.tpeak;
+  a.tphist = st.tphist;
+  memcpy(a.tp4, p.tp4, sizeof(a.tp4));
+  memcpy(a.tp2, p.tp2, sizeof(a.tp2));
   a.active_mask = p.do_filter ? p.active_mask : 0;
   a.n_streams = (unsigned)st.n_streams;
   a.n_tiles = (unsigned)n_tiles;
@@ -556,11 +581,11 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   size_t n_ctas = (st.n_streams + kRows - 1) / kRows;
   if (n_ctas < (size_t)sms && st.n_streams >= (size_t)sms) n_ctas = sms;  // spread rows over every SM
-  cudaError_t e = C == 1 ? launch_tile_cfg<1, kTileT, kTileF>(tmap, a, (unsigned)n_ctas, s)
-                         : launch_tile_cfg<2, kTileT, kTileF>(tmap, a, (unsigned)n_ctas, s);
+  const int tpf = p.do_true_peak ? p.tp_factor : 0;
+  cudaError_t e = C == 1 ? launch_tile_c<1>(tmap, a, (unsigned)n_ctas, tpf, s) : launch_tile_c<2>(tmap, a, (unsigned)n_ctas, tpf, s);
   if (e) return e;
   if (launches) ++*launches;
-  *consumed = n_tiles * kTileF;
+  *consumed = n_tiles * tile_f;
   return cudaSuccess;
 }
 

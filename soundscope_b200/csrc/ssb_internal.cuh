@@ -23,6 +23,7 @@ constexpr int kTpHist = 24;          // input samples of true-peak history kept 
 struct LoudParams {
   double b[5];
   double a[5];          // a[0] == 1, unused
+  double na[5];         // -a[i]: constant-bank DFMA operands (a negated register operand costs a third RF read)
   float tp4[3][12];     // factor-4 interpolator, phases 1..3, tap t multiplies x[n-t]
   float tp2[24];        // factor-2 interpolator, phase 1
   int tp_factor;        // 0 (none), 2 or 4 — ebur128's rate rule

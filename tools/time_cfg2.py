@@ -1,0 +1,29 @@
+"""Quick timing of the cfg2 loudness step (device-resident), for kernel tuning: prints ms/step and GB/s."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import soundscope_b200 as S
+from bench import make_input_device, N_STREAMS, FRAMES, CHANNELS, RATE
+
+n = int(os.environ.get("N_STREAMS", N_STREAMS))
+mode = S.MODE_ALL if "--all" in sys.argv else S.MODE_LOUDNESS
+torch.cuda.set_device(0)
+dev = torch.device("cuda", 0)
+an = S.BatchAnalyzer(n, CHANNELS, RATE, mode, device=0)
+xs = [make_input_device(torch, n, FRAMES, 1234 + i, dev) for i in range(2)]
+for i in range(4):
+    an.add_frames_device(xs[i & 1])
+torch.cuda.synchronize()
+an.profile(True)
+K = 20
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(K):
+    an.add_frames_device(xs[i & 1])
+e1.record()
+torch.cuda.synchronize()
+ms, cnt = an.profile_read()
+step = e0.elapsed_time(e1) / K
+b = n * FRAMES * CHANNELS * 4
+print(f"SSB_TILE_F={os.environ.get('SSB_TILE_F','256')} n={n} mode={'all' if mode==S.MODE_ALL else 'loudness'}: step {step*1e3:.1f} us, filter kernel {ms/cnt*1e3:.1f} us "
+      f"-> {b/(ms/cnt*1e-3)/1e9:.0f} GB/s ({b/(ms/cnt*1e-3)/1e9/6572.9*100:.1f}% of 6572.9), {n*FRAMES*CHANNELS/(step*1e-3):.3e} samples/s")
