@@ -263,7 +263,25 @@ int32_t get_plan(ssb_analyzer* h, size_t n, uint32_t rate, FftPlan** out) {
     CK(cudaMalloc(&p.d_twiddle, tw.size() * sizeof(float2)));
     CK(cudaMemcpyAsync(p.d_window, w.data(), n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(p.d_twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));  // w / tw are locals
+    std::vector<float2> lo(64), hi(n >= 64 ? n / 64 : 0);
+    auto wn = [&](size_t e) {
+      const size_t m = e % n;
+      if (m == 0) return make_float2(1.f, 0.f);
+      if (4 * m == n) return make_float2(0.f, -1.f);
+      if (2 * m == n) return make_float2(-1.f, 0.f);
+      if (4 * m == 3 * n) return make_float2(0.f, 1.f);
+      const double ang = 2.0 * M_PI * (double)m / (double)n;
+      return make_float2((float)cos(ang), (float)-sin(ang));
+    };
+    if (n >= 1024) {  // the fast kernel serves transform lengths >= 512
+      for (size_t i = 0; i < 64; i++) lo[i] = wn(i);
+      for (size_t i = 0; i < hi.size(); i++) hi[i] = wn(64 * i);
+      CK(cudaMalloc(&p.d_tw_lo, lo.size() * sizeof(float2)));
+      CK(cudaMalloc(&p.d_tw_hi, hi.size() * sizeof(float2)));
+      CK(cudaMemcpyAsync(p.d_tw_lo, lo.data(), lo.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(p.d_tw_hi, hi.data(), hi.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));  // w / tw / lo / hi are locals
     it = h->plans.emplace(key, p).first;
   }
   *out = &it->second;
@@ -353,6 +371,8 @@ void ssb_analyzer_destroy(ssb_analyzer* h) {
   for (auto& kv : h->plans) {
     cudaFree(kv.second.d_window);
     cudaFree(kv.second.d_twiddle);
+    cudaFree(kv.second.d_tw_lo);
+    cudaFree(kv.second.d_tw_hi);
   }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

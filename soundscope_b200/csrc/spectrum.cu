@@ -7,6 +7,7 @@
 // whose digit-reversed result is read back only at the kept bins; the store stage fuses the real
 // split (two real spectra from one complex transform for mid/side; the packed N/2-point trick for
 // mono), |X| -> scale_to_dbfs (analyzer.rs:11-27) and the spectrum-analyzer argument checks.
+#include "fft_core.cuh"
 #include "ssb_internal.cuh"
 
 namespace ssb {
@@ -79,6 +80,17 @@ __device__ __forceinline__ float mag_to_dbfs(float re, float im, float nf, int* 
   const float scaled = __fdiv_rn(__fmul_rn(m, 4.0f), nf);
   const float db = 20.0f * log10f(scaled);
   if (!isfinite(db)) *bad = 1;
+  return db;
+}
+
+// Same formula for the batched kernel: the division by N is an exact power-of-two scaling, and log10 is taken
+// as log2 * log10(2) on the SFU (MUFU.LG2, abs error < 2^-22 in log2 units, i.e. < 2e-6 dB: two orders
+// below the 1e-4 dB / 1e-5 relative tolerance of the path); sqrt.approx (2 ulp) sits below that too.
+__device__ __forceinline__ float mag_to_dbfs_fast(float re, float im, float four_over_n, unsigned* mx) {
+  float m;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(m) : "f"(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im))));
+  const float db = m == 0.0f ? -150.0f : 6.02059991327962390f * __log2f(m * four_over_n);
+  *mx = max(*mx, __float_as_uint(db) & 0x7fffffffu);  // >= 0x7f800000 at the end: a non-finite dB (ScalingError)
   return db;
 }
 
@@ -188,11 +200,197 @@ k_fft(const float* __restrict__ in, unsigned N, const float* __restrict__ window
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_fft_fast: the same window -> dB pipeline on the three-stage register-butterfly core (fft_core.cuh),
+// for transform lengths M = 512 .. 16384.  One CTA (128 threads) per window, up to three CTAs per SM so
+// one window's HBM load overlaps another's butterflies.  Twiddle tables are staged into shared memory by
+// a TMA bulk copy (cp.async.bulk + mbarrier) issued before the input load, so they land underneath it.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int R1>
+__device__ __forceinline__ void run_stage1(float2* z, unsigned M, unsigned N, const FftTwiddle& tw) {
+  for (unsigned j = threadIdx.x; j < M / R1; j += blockDim.x) fft_stage1<R1>(z, M, N, tw, j);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(128, 3)
+k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ window,
+           const float2* __restrict__ g_lo, const float2* __restrict__ g_hi, unsigned k_first, unsigned n_bins,
+           float* __restrict__ db_out, unsigned planes_out, unsigned plane_off, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  const unsigned M = (LAYOUT == 1) ? N : (N >> 1);
+  const unsigned n_hi = N >> 6;
+  float2* s_lo = reinterpret_cast<float2*>(fsm);                       // [64]
+  float2* s_hi = s_lo + 64;                                            // [N/64]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_hi + n_hi);            // 8-byte aligned: (64 + n_hi) * 8
+  int* s_flags = reinterpret_cast<int*>(bar + 1);                      // [4]
+  float2* z = reinterpret_cast<float2*>(s_flags + 4);                  // [M + M/32]
+  const unsigned w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_flags[0] = s_flags[1] = s_flags[2] = 0;
+    const unsigned bytes = (64 + n_hi) * (unsigned)sizeof(float2);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sm_u32(s_lo)), "l"(g_lo), "r"(64u * (unsigned)sizeof(float2)), "r"(sm_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sm_u32(s_hi)), "l"(g_hi), "r"(n_hi * (unsigned)sizeof(float2)), "r"(sm_u32(bar)) : "memory");
+  }
+  __syncthreads();
+
+  // largest |bit pattern| seen per plane: > 0x7f800000 means a NaN is present, == means an infinity (and no
+  // NaN) — exactly the precedence of spectrum-analyzer's checks (NaN first, then infinity)
+  unsigned mx0 = 0, mx1 = 0;
+  const float four_over_n = 4.0f / (float)N;  // exact: N is a power of two
+  // loads are issued in batches of U per thread before any is consumed: the window streams in with
+  // U * 128 independent 8/16-byte requests in flight per CTA instead of one per thread
+  if (LAYOUT == 1) {
+    constexpr int U = 8;  // N >= 1024 = U * 128
+    const float2* src = reinterpret_cast<const float2*>(in) + (size_t)w * N;
+    for (unsigned base = 0; base < N; base += U * nt) {
+      float2 lr[U];
+      float wn[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        lr[u] = __ldg(&src[base + u * nt + tid]);
+        wn[u] = __ldg(&window[base + u * nt + tid]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const float mid = __fmul_rn(__fadd_rn(lr[u].x, lr[u].y), 0.5f);
+        const float side = __fmul_rn(__fsub_rn(lr[u].x, lr[u].y), 0.5f);
+        const float2 v = make_float2(__fmul_rn(wn[u], mid), __fmul_rn(wn[u], side));
+        mx0 = max(mx0, __float_as_uint(v.x) & 0x7fffffffu);
+        mx1 = max(mx1, __float_as_uint(v.y) & 0x7fffffffu);
+        z[fft_pad(base + u * nt + tid)] = v;
+      }
+    }
+  } else {
+    constexpr int U = 4;  // M >= 512 = U * 128
+    for (unsigned base = 0; base < M; base += U * nt) {
+      float x0[U], x1[U];
+      float2 wn[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const unsigned m = base + u * nt + tid;
+        if (LAYOUT == 0) {
+          const float2 p = __ldg(reinterpret_cast<const float2*>(in + (size_t)w * N) + m);
+          x0[u] = p.x; x1[u] = p.y;
+        } else {
+          const float4 p = __ldg(reinterpret_cast<const float4*>(in + (size_t)w * N * 2) + m);
+          if (LAYOUT == 2) { x0[u] = __fmul_rn(__fadd_rn(p.x, p.y), 0.5f); x1[u] = __fmul_rn(__fadd_rn(p.z, p.w), 0.5f); }
+          else { x0[u] = __fmul_rn(__fsub_rn(p.x, p.y), 0.5f); x1[u] = __fmul_rn(__fsub_rn(p.z, p.w), 0.5f); }
+        }
+        wn[u] = __ldg(reinterpret_cast<const float2*>(window) + m);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const float2 v = make_float2(__fmul_rn(wn[u].x, x0[u]), __fmul_rn(wn[u].y, x1[u]));
+        mx0 = max(mx0, max(__float_as_uint(v.x), __float_as_uint(v.y)) & 0x7fffffffu);
+        z[fft_pad(base + u * nt + tid)] = v;
+      }
+    }
+  }
+  if (mx0 >= 0x7f800000u) atomicOr(mx0 > 0x7f800000u ? &s_flags[0] : &s_flags[1], 1);
+  if (mx1 >= 0x7f800000u) atomicOr(mx1 > 0x7f800000u ? &s_flags[0] : &s_flags[1], 2);
+  // twiddles have landed?
+  {
+    unsigned ok = 0, spins = 0;
+    while (!ok) {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(ok) : "r"(sm_u32(bar)) : "memory");
+      if (!ok && ++spins > (1u << 26)) __trap();
+    }
+  }
+  __syncthreads();
+
+  const FftTwiddle tw{s_lo, s_hi};
+  switch (M >> 9) {
+    case 2: run_stage1<2>(z, M, N, tw); break;
+    case 4: run_stage1<4>(z, M, N, tw); break;
+    case 8: run_stage1<8>(z, M, N, tw); break;
+    case 16: run_stage1<16>(z, M, N, tw); break;
+    case 32: run_stage1<32>(z, M, N, tw); break;
+    default: break;  // M == 512: no first stage
+  }
+  __syncthreads();
+  for (unsigned t = tid; t < (M >> 4); t += nt) fft_stage2(z, N, tw, t);
+  __syncthreads();
+  for (unsigned t = tid; t < (M >> 5); t += nt) fft_stage3(z, t);
+  __syncthreads();
+
+  unsigned mxo = 0;
+  const unsigned r1s = 31u - (unsigned)__clz(M >> 9);  // log2(R1)
+  if (LAYOUT == 1) {
+    float* o_mid = db_out + ((size_t)w * planes_out + 0) * n_bins;
+    float* o_side = db_out + ((size_t)w * planes_out + 1) * n_bins;
+    for (unsigned i = tid; i < n_bins; i += nt) {
+      const unsigned k = k_first + i;
+      const float2 a = z[fft_position(k, r1s)];
+      const float2 b = z[fft_position((N - k) & (N - 1), r1s)];
+      const float mr = 0.5f * (a.x + b.x), mi = 0.5f * (a.y - b.y);
+      const float sr = 0.5f * (a.y + b.y), si = -0.5f * (a.x - b.x);
+      o_mid[i] = mag_to_dbfs_fast(mr, mi, four_over_n, &mxo);
+      o_side[i] = mag_to_dbfs_fast(sr, si, four_over_n, &mxo);
+    }
+  } else {
+    float* o = db_out + ((size_t)w * planes_out + plane_off) * n_bins;
+    for (unsigned i = tid; i < n_bins; i += nt) {
+      const unsigned k = k_first + i;
+      float xr, xi;
+      if (k == M) {
+        const float2 z0 = z[fft_position(0, r1s)];
+        xr = z0.x - z0.y; xi = 0.0f;
+      } else {
+        const float2 a = z[fft_position(k, r1s)];
+        const float2 b = z[fft_position(M - k, r1s)];
+        const float sr = 0.5f * (a.x + b.x), si = 0.5f * (a.y - b.y);
+        const float dr = 0.5f * (a.x - b.x), di = 0.5f * (a.y + b.y);
+        const float2 wk = fft_twiddle(tw, k);  // W_N^k
+        xr = sr + (wk.x * di + wk.y * dr);
+        xi = si + (wk.y * di - wk.x * dr);
+      }
+      o[i] = mag_to_dbfs_fast(xr, xi, four_over_n, &mxo);
+    }
+  }
+  if (mxo >= 0x7f800000u) atomicOr(&s_flags[2], 1);
+  __syncthreads();
+  if (status && tid == 0) {
+    if (LAYOUT == 1) {
+      for (int pl = 0; pl < 2; pl++) {
+        int32_t st = SSB_OK;
+        if (s_flags[0] & (1 << pl)) st = SSB_ERR_FFT_NAN;
+        else if (s_flags[1] & (1 << pl)) st = SSB_ERR_FFT_INF;
+        else if (s_flags[2]) st = SSB_ERR_FFT_SCALING;
+        status[(size_t)w * planes_out + pl] = st;
+      }
+    } else {
+      int32_t st = SSB_OK;
+      if (s_flags[0]) st = SSB_ERR_FFT_NAN;
+      else if (s_flags[1]) st = SSB_ERR_FFT_INF;
+      else if (s_flags[2]) st = SSB_ERR_FFT_SCALING;
+      status[(size_t)w * planes_out + plane_off] = st;
+    }
+  }
+}
+
 template <int LAYOUT>
 static cudaError_t launch_fft_layout(const FftPlan& plan, const float* d_in, size_t n_windows, float* d_db,
                                      unsigned planes_out, unsigned plane_off, int32_t* d_status, cudaStream_t s) {
   const unsigned N = (unsigned)plan.n;
   const unsigned M = (LAYOUT == 1) ? N : (N >> 1);
+  if (M >= 512 && plan.d_tw_lo) {
+    const size_t fsmem = (size_t)(64 + (N >> 6)) * sizeof(float2) + 8 + 16 + (size_t)(M + (M >> 5) + 1) * sizeof(float2);
+    cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    if (fe) return fe;
+    k_fft_fast<LAYOUT><<<(unsigned)n_windows, 128, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo, plan.d_tw_hi,
+                                                               (unsigned)plan.k_first, (unsigned)plan.n_bins, d_db,
+                                                               planes_out, plane_off, d_status);
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)(M ? M : 1) * sizeof(float2);
   cudaError_t e = cudaFuncSetAttribute(k_fft<LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e) return e;

@@ -93,6 +93,8 @@ struct FftPlan {
   size_t k_first = 0, n_bins = 0;
   float* d_window = nullptr;   // [n] Hann multipliers
   float2* d_twiddle = nullptr; // [n/2] exp(-j*2*pi*k/n)
+  float2* d_tw_lo = nullptr;   // [64]   W_n^i           (two-level table of the fast kernel)
+  float2* d_tw_hi = nullptr;   // [n/64] W_n^(64 i)
 };
 cudaError_t launch_fft(const FftPlan& plan, const float* d_in, int layout, size_t n_windows,
                        float* d_db_out, int32_t* d_status, cudaStream_t s, uint64_t* launches);

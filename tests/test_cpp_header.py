@@ -1,0 +1,45 @@
+"""The C++ host-side mirror (include/soundscope_b200.hpp) compiles against the C ABI header and links with
+the shared library (no GPU needed: compile + link only; running it needs a device and is covered by the
+ctypes path, which makes the same calls)."""
+import os
+import subprocess
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+PROG = r'''
+#include "soundscope_b200.hpp"
+#include <cstdio>
+int main() {
+  try {
+    soundscope::Analyzer a;
+    a.create_loudness_meter(2, 48000);
+    std::vector<float> x(16384, 0.0f);
+    a.add_samples(x);
+    auto fft = a.get_fft(x);
+    auto wf = a.get_waveform(x, 1.0);
+    auto ms = a.get_mid_and_side_samples(x);
+    std::printf("%f %zu %zu %zu\n", a.get_integrated_lufs(), fft.size(), wf.size(), ms.first.size());
+  } catch (const soundscope::Error& e) {
+    std::printf("error %d %s\n", e.code, e.what());
+    return e.code == SSB_ERR_NO_DEVICE ? 42 : 1;
+  }
+  return 0;
+}
+'''
+
+
+def test_cpp_mirror_compiles_links_and_fails_loudly_without_gpu(ssb):
+    import torch
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.cpp")
+        exe = os.path.join(d, "t")
+        open(src, "w").write(PROG)
+        libdir = os.path.dirname(ssb.library_path())
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                               "-L", libdir, "-lsoundscope_b200", f"-Wl,-rpath,{libdir}"])
+        r = subprocess.run([exe], capture_output=True, text=True)
+        if torch.cuda.is_available():
+            assert r.returncode == 0, r.stdout + r.stderr
+        else:
+            assert r.returncode == 42, r.stdout + r.stderr   # SSB_ERR_NO_DEVICE: no CPU fallback

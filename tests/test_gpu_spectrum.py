@@ -24,9 +24,11 @@ def assert_db_close(got_db, want_db):
     got_db, want_db = np.asarray(got_db, dtype=np.float64), np.asarray(want_db, dtype=np.float64)
     mg, mw = 10 ** (got_db / 20), 10 ** (want_db / 20)
     peak = mw.max()
-    assert np.max(np.abs(mg - mw)) <= 1e-5 * peak
+    rel = np.max(np.abs(mg - mw)) / peak
+    assert rel <= 1e-5, f"max |dmag| / peak = {rel:.3e}"
     near = want_db >= want_db.max() - 20.0
-    assert np.max(np.abs(got_db[near] - want_db[near])) <= 1e-4
+    ddb = np.abs(got_db[near] - want_db[near])
+    assert ddb.max() <= 1e-4, f"max |d dB| within 20 dB of the peak = {ddb.max():.3e} at level {want_db[near][ddb.argmax()] - want_db.max():.1f} dB (rel mag err {rel:.3e})"
 
 
 def test_reference_fft_tests_on_gpu(ssb, oracle, cuda):
