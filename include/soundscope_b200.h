@@ -148,6 +148,19 @@ enum { SSB_FFT_MONO = 0, SSB_FFT_MID_SIDE = 1 };
 int32_t ssb_fft_batch_device(ssb_analyzer* h, const float* d_in, int32_t layout, size_t n,
                              size_t n_windows, float* d_db_out, int32_t* d_status);
 
+/* ---- one player tick in one call (north_star's `Analyzer::process`) ------- */
+/* What tui.rs:1482-1552 (analyze_audio_file_samples) does per playback-position message, fused:
+ *   mid/side of the last n_fft stereo frames -> get_fft(mid), get_fft(side)   (tui.rs:1488-1515)
+ *   add_samples(last lufs_samples interleaved samples) -> get_shortterm_lufs  (tui.rs:1528-1543)
+ * `tail` holds the last n_fft stereo frames (2*n_fft interleaved f32, HOST); the meter is fed the final
+ * lufs_samples of it (the reference passes 16384).  One H2D copy, three kernels, one D2H copy.
+ * xy_mid / xy_side receive (x, dB) pairs like ssb_get_fft (cap pairs each).  fft_status / lufs_status return
+ * the per-part status so the caller can reproduce the reference's independent error handling
+ * (`vec![(0., 0.)]` on an FFT error, error popup on a meter error).  Needs a stereo handle. */
+int32_t ssb_process_tick(ssb_analyzer* h, const float* tail, size_t n_fft, size_t lufs_samples,
+                         double* xy_mid, double* xy_side, size_t cap, size_t* n_points,
+                         double* shortterm_lufs, int32_t* fft_status, int32_t* lufs_status);
+
 /* ---- waveform + mid/side (stateless) ------------------------------------------------------ */
 /* Analyzer::get_waveform (analyzer.rs:107-137): HOST samples -> (i, min), (i, max) pairs. */
 int32_t ssb_get_waveform(ssb_analyzer* h, const float* samples, size_t len, double waveform_window,
@@ -167,7 +180,8 @@ int32_t ssb_profile_enable(ssb_analyzer* h, int32_t on);
 /* synchronises, then returns and clears the accumulated filter-kernel time and launch count */
 int32_t ssb_profile_read(ssb_analyzer* h, double* filter_ms, uint64_t* filter_launches);
 
-/* tests only: route every add_frames through the generic (thread-per-channel) kernel */
+/* tests only: pick the filter kernel — 0 automatic, 1 generic (thread per channel), 2 serial many-streams
+ * kernel, 3 time-segmented tile kernel */
 int32_t ssb_debug_force_generic(ssb_analyzer* h, int32_t on);
 
 /* ---- introspection used by the tests ------------------------------------------------------ */

@@ -109,6 +109,22 @@ class Analyzer:
         check(self._h, lib().ssb_calculate_integrated_lufs(self._h, channels, p, a.size, C.byref(out), C.byref(some)))
         return out.value if some.value else None
 
+    def process_tick(self, tail, lufs_samples=16384):
+        """One player tick (reference src/tui.rs:1482-1552) in one call: `tail` = the last n_fft stereo frames,
+        interleaved.  Returns (mid_fft, side_fft, shortterm_lufs, fft_status, lufs_status); the FFT arrays are
+        None when the reference's get_fft would return Err (it then shows `vec![(0., 0.)]`)."""
+        a, p = _f32(tail)
+        n_fft = a.size // 2
+        cap = n_fft // 2 + 1
+        mid = np.empty((max(cap, 1), 2), dtype=np.float64)
+        side = np.empty((max(cap, 1), 2), dtype=np.float64)
+        n, st = C.c_size_t(0), C.c_double(0)
+        fs, ls = C.c_int32(0), C.c_int32(0)
+        check(self._h, lib().ssb_process_tick(self._h, p, n_fft, lufs_samples, mid.ctypes.data, side.ctypes.data, cap,
+                                               C.byref(n), C.byref(st), C.byref(fs), C.byref(ls)))
+        ok = fs.value == 0
+        return (mid[: n.value] if ok else None, side[: n.value] if ok else None, st.value, fs.value, ls.value)
+
     # introspection (tests)
     def filter_coeffs(self):
         b, a = np.zeros(5), np.zeros(5)

@@ -41,6 +41,10 @@ class BatchAnalyzer:
     def force_generic(self, on=True):
         check(self._h, lib().ssb_debug_force_generic(self._h, 1 if on else 0))
 
+    def force_kernel(self, which):
+        """tests: 0 automatic, 1 generic, 2 serial many-streams kernel, 3 time-segmented tile kernel"""
+        check(self._h, lib().ssb_debug_force_generic(self._h, int(which)))
+
     def profile(self, on=True):
         check(self._h, lib().ssb_profile_enable(self._h, 1 if on else 0))
 

@@ -45,7 +45,7 @@ struct ssb_analyzer {
   std::map<std::pair<size_t, uint32_t>, std::pair<std::vector<double>, std::vector<double>>> axes;
 
   uint64_t launches = 0;
-  bool force_generic = false;  // tests: route everything through the generic kernel
+  int force_kernel = 0;  // tests: 0 auto, 1 generic kernel, 2 serial rows kernel, 3 time-segmented tile kernel
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
@@ -207,9 +207,9 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
       CK(cudaEventRecord(ev0, h->stream));
     }
     size_t tiled = 0;
-    if (!h->force_generic && tile_path_usable(h->lp, h->st, d_in + done * C, n, in_stride_frames))
+    if (h->force_kernel != 1 && tile_path_usable(h->lp, h->st, d_in + done * C, n, in_stride_frames))
       CK(launch_loudness_tile(h->lp, h->st, d_in + done * C, n, in_stride_frames, pos, bucket0, h->stream,
-                              &h->launches, &tiled));
+                              &h->launches, &tiled, h->force_kernel));
     if (tiled < n) {
       const uint64_t t2 = h->total_frames + tiled;
       CK(launch_loudness_generic(h->lp, h->st, d_in + (done + tiled) * C, n - tiled, in_stride_frames,
@@ -689,6 +689,75 @@ int32_t ssb_get_fft(ssb_analyzer* h, const float* samples, size_t n, double* xy_
   return SSB_OK;
 }
 
+int32_t ssb_process_tick(ssb_analyzer* h, const float* tail, size_t n_fft, size_t lufs_samples, double* xy_mid,
+                         double* xy_side, size_t cap, size_t* n_points, double* shortterm_lufs, int32_t* fft_status,
+                         int32_t* lufs_status) {
+  if (!h || !tail || !n_points || !shortterm_lufs || !fft_status || !lufs_status) return SSB_ERR_INVALID_ARG;
+  if (h->channels != 2 || h->n_streams != 1) return fail(h, SSB_ERR_INVALID_ARG, "process_tick needs one stereo stream");
+  if (lufs_samples > 2 * n_fft) return fail(h, SSB_ERR_INVALID_ARG, "lufs_samples exceeds the tail");
+  *n_points = 0;
+  *fft_status = fft_shape_check(n_fft, h->rate);
+  *lufs_status = (lufs_samples % 2 != 0) ? SSB_ERR_NOMEM : SSB_OK;  // add_frames_f32: ragged -> Error::NoMem
+  DeviceGuard g(h->device);
+  FftPlan* plan = nullptr;
+  size_t nb = 0;
+  if (*fft_status == SSB_OK) {
+    int32_t rc = get_plan(h, n_fft, h->rate, &plan);
+    if (rc) return rc;
+    nb = plan->n_bins;
+    *n_points = nb;
+    if (nb > cap || !xy_mid || !xy_side) return fail(h, SSB_ERR_CAPACITY, "process_tick: need room for %zu points", nb);
+  }
+  const size_t in_bytes = 2 * n_fft * sizeof(float);
+  const size_t out_off = (in_bytes + 255) & ~(size_t)255;
+  const size_t db_bytes = 2 * nb * sizeof(float) + 2 * sizeof(int32_t);
+  const size_t stride = 4 + 2 * (size_t)h->channels;
+  int32_t rc = ensure_scratch(h, out_off + db_bytes + 256);
+  if (rc) return rc;
+  float* d_in = h->d_scratch;
+  float* d_db = reinterpret_cast<float*>(reinterpret_cast<char*>(h->d_scratch) + out_off);
+  int32_t* d_status = reinterpret_cast<int32_t*>(d_db + 2 * nb);
+  CK(cudaMemcpyAsync(d_in, tail, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  if (plan) {
+    CK(launch_fft(*plan, d_in, SSB_FFT_MID_SIDE, 1, d_db, d_status, h->stream, &h->launches));
+    CK(cudaMemcpyAsync(h->h_scratch, d_db, db_bytes, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (*lufs_status == SSB_OK && lufs_samples) {
+    rc = feed_device(h, d_in + (2 * n_fft - lufs_samples), lufs_samples / 2, lufs_samples / 2);
+    if (rc) return rc;
+  }
+  const int aligned = (h->total_frames % h->lp.s100) == 0;
+  if (!h->st.ring && !aligned) *lufs_status = *lufs_status ? *lufs_status : SSB_ERR_UNALIGNED_QUERY;
+  CK(launch_results(h->gp, h->st, h->total_frames / h->lp.s100, aligned, h->ring_pos, h->mode, h->d_results, h->stream,
+                    &h->launches));
+  CK(cudaMemcpyAsync(h->h_results, h->d_results, stride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->results_valid = true;
+  *shortterm_lufs = h->h_results[1];
+  if ((h->mode & SSB_MODE_S) != SSB_MODE_S && *lufs_status == SSB_OK) *lufs_status = SSB_ERR_INVALID_MODE;
+  if (plan) {
+    const float* db = static_cast<const float*>(h->h_scratch);
+    const int32_t* st = reinterpret_cast<const int32_t*>(db + 2 * nb);
+    *fft_status = st[0] ? st[0] : st[1];
+    auto key = std::make_pair(n_fft, h->rate);
+    auto it = h->axes.find(key);
+    if (it == h->axes.end()) {
+      std::vector<double> x, t;
+      fft_axis(n_fft, h->rate, x, t, nullptr);
+      it = h->axes.emplace(key, std::make_pair(std::move(x), std::move(t))).first;
+    }
+    const std::vector<double>& ax = it->second.first;
+    const std::vector<double>& tilt = it->second.second;
+    for (size_t i = 0; i < nb; i++) {
+      xy_mid[2 * i] = ax[i];
+      xy_mid[2 * i + 1] = (double)db[i] + tilt[i];
+      xy_side[2 * i] = ax[i];
+      xy_side[2 * i + 1] = (double)db[nb + i] + tilt[i];
+    }
+  }
+  return SSB_OK;
+}
+
 static size_t waveform_window_columns(double waveform_window, size_t len, size_t* window_out) {
   const double w = waveform_window * 1000.;
   size_t window = 0;  // Rust `as usize` saturates; NaN -> 0
@@ -779,7 +848,7 @@ int32_t ssb_mid_side(ssb_analyzer* h, const float* interleaved, size_t len, floa
 
 int32_t ssb_debug_force_generic(ssb_analyzer* h, int32_t on) {
   if (!h) return SSB_ERR_INVALID_ARG;
-  h->force_generic = on != 0;
+  h->force_kernel = on;
   return SSB_OK;
 }
 

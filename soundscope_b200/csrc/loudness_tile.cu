@@ -81,6 +81,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
+// the same wait for a fully active warp: the exit test is a vote, so the branch is warp-uniform and the code
+// after it stays eligible for the uniform datapath (coefficients in uniform registers instead of a third
+// register operand on every recursion DFMA)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, unsigned parity) {
+  unsigned spins = 0;
+  while (!__all_sync(0xffffffffu, mbar_try(bar, parity))) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -235,10 +244,11 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
   for (int t = 0; t < TPW; t++) hist[t] = (TPF != 0 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
   unsigned pos_tile = a.pos0;  // position of the tile start inside the bucket in progress
+  const double na1 = a.na[1], na2 = a.na[2], na3 = a.na[3], na4 = a.na[4];
 
   for (unsigned tile = 0; tile < a.n_tiles; tile++) {
     const unsigned s = tile % kStages;
-    mbar_wait(&full[s], (tile / kStages) & 1);
+    mbar_wait_warp(&full[s], (tile / kStages) & 1);
     const unsigned char* line0 = stages + (size_t)s * STAGE_BYTES + ((size_t)(k * SEG_CHUNKS) * kRows + r) * 128;
 
     // ---- pass 1: zero-state recursion over my segment -> z (4 DFMA / sample) ----
@@ -252,10 +262,10 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
         for (int f = 0; f < FPQ; f++) {
           const double x = SSB_CVT(pick<C>(q, f, c));
-          double t = fma(a.na[4], z4, x);
-          t = fma(a.na[3], z3, t);
-          t = fma(a.na[2], z2, t);
-          const double z0 = fma(a.na[1], z1, t);
+          double t = fma(na4, z4, x);
+          t = fma(na3, z3, t);
+          t = fma(na2, z2, t);
+          const double z0 = fma(na1, z1, t);
           z4 = z3; z3 = z2; z2 = z1; z1 = z0;
         }
       }
@@ -422,6 +432,319 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// k_loudness_rows: the many-streams variant (>= 16384 streams per GPU, BASELINE config 4).  With that many
+// independent recursions there is no need to split time: one lane per (stream, channel) runs the reference's
+// recursion serially (10 DFMA + 1 F2F per sample: no zero-state pass, no hand-off), on the same TMA /
+// SWIZZLE_128B staging with [128 streams x 64 frames] tiles and a register-resident true-peak history.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowsSerial = 128;
+constexpr int kSerialF = 64;
+
+template <int C, int TPF>
+__global__ void __launch_bounds__(kRowsSerial* C + 32, 1)
+k_loudness_rows(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileArgs a) {
+  constexpr int F = kSerialF;
+  constexpr int RW = 32 / C;                       // rows per warp
+  constexpr int NW = kRowsSerial / RW;             // compute warps
+  constexpr int CHUNKS = F * C / 32;               // 128-byte lines per row per stage
+  constexpr int FPQ = 4 / C;
+  constexpr unsigned STAGE_BYTES = CHUNKS * kRowsSerial * 128;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* stages = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+  uint64_t* empty = full + kStages;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const unsigned row0 = blockIdx.x * (unsigned)kRowsSerial;
+  const unsigned nrows = min((unsigned)kRowsSerial, a.n_streams - row0);
+  const unsigned live_warps = (nrows + RW - 1) / RW;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], live_warps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    if (lane == 0 && live_warps > 0) {
+      for (unsigned tile = 0; tile < a.n_tiles; tile++) {
+        const unsigned s = tile % kStages;
+        if (tile >= (unsigned)kStages) mbar_wait(&empty[s], ((tile / kStages) - 1) & 1);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        tma_load_3d(stages + (size_t)s * STAGE_BYTES, &tmap, &full[s], 0, (int)row0, (int)(tile * CHUNKS));
+      }
+    }
+    return;
+  }
+  if ((unsigned)warp >= live_warps) return;
+
+  const int rr = lane / C;
+  const int c = lane - rr * C;
+  const int r = warp * RW + rr;
+  const bool row_ok = (unsigned)r < nrows;
+  const bool live = row_ok && ((a.active_mask >> c) & 1ull);
+  const size_t gidx = ((size_t)(row0 + r)) * C + c;
+  const unsigned key = r & 7;
+
+  double v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+  if (live) {
+    const double* f = a.filt + gidx * 4;
+    v1 = f[0]; v2 = f[1]; v3 = f[2]; v4 = f[3];
+  }
+  unsigned slot = a.slot0;
+  double acc = (live && a.pos0 > 0) ? a.bucket[gidx * kNB + slot] : 0.0;
+  float sp = 0.f, tp = 0.f;
+  constexpr int TPW = TPF == 4 ? 11 : (TPF == 2 ? 23 : 1);
+  float w[TPW];
+#pragma unroll
+  for (int t = 0; t < TPW; t++) w[t] = (TPF != 0 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
+  unsigned pos = a.pos0;  // frames already in the bucket in progress
+
+  for (unsigned tile = 0; tile < a.n_tiles; tile++) {
+    const unsigned s = tile % kStages;
+    mbar_wait_warp(&full[s], (tile / kStages) & 1);
+    const unsigned char* line0 = stages + (size_t)s * STAGE_BYTES + (size_t)r * 128;
+    const unsigned to_boundary = a.s100 - pos;   // > F: the bucket does not end inside this tile
+    if (to_boundary > (unsigned)F) {
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ch++) {
+        const unsigned char* line = line0 + (size_t)ch * kRowsSerial * 128;
+#pragma unroll
+        for (int qi = 0; qi < 8; qi++) {
+          const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
+#pragma unroll
+          for (int f = 0; f < FPQ; f++) {
+            const float xf = pick<C>(q, f, c);
+            sp = fmaxf(sp, fabsf(xf));
+            SSB_FILTER_STEP(SSB_CVT(xf))
+            acc = fma(y_, y_, acc);
+          }
+        }
+      }
+      pos += F;
+    } else {
+      int i = 0;
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ch++) {
+        const unsigned char* line = line0 + (size_t)ch * kRowsSerial * 128;
+#pragma unroll 1
+        for (int qi = 0; qi < 8; qi++) {
+          const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
+#pragma unroll
+          for (int f = 0; f < FPQ; f++, i++) {
+            const float xf = pick<C>(q, f, c);
+            sp = fmaxf(sp, fabsf(xf));
+            SSB_FILTER_STEP(SSB_CVT(xf))
+            acc = fma(y_, y_, acc);
+            if (i + 1 == (int)to_boundary) {   // the bucket in progress is complete
+              if (live) a.bucket[gidx * kNB + slot] = acc;
+              acc = 0.0;
+              slot = (slot + 1) % kNB;
+            }
+          }
+        }
+      }
+      pos = (unsigned)F - to_boundary;
+    }
+    if (TPF != 0) {
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ch++) {
+        const unsigned char* line = line0 + (size_t)ch * kRowsSerial * 128;
+#pragma unroll
+        for (int qi = 0; qi < 8; qi++) {
+          const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
+#pragma unroll
+          for (int f = 0; f < FPQ; f++) {
+            const float xf = pick<C>(q, f, c);
+            if (TPF == 4) {
+#pragma unroll
+              for (int ph = 0; ph < 3; ph++) {
+                float accf = xf * a.tp4[ph][0];
+#pragma unroll
+                for (int t = 1; t < 12; t++) accf = fmaf(w[t - 1], a.tp4[ph][t], accf);
+                tp = fmaxf(tp, fabsf(accf));
+              }
+            } else {
+              float accf = xf * a.tp2[0];
+#pragma unroll
+              for (int t = 1; t < 24; t++) accf = fmaf(w[t - 1], a.tp2[t], accf);
+              tp = fmaxf(tp, fabsf(accf));
+            }
+#pragma unroll
+            for (int t = TPW - 1; t > 0; t--) w[t] = w[t - 1];
+            w[0] = xf;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  if (live) {
+    a.bucket[gidx * kNB + slot] = acc;
+    double* f = a.filt + gidx * 4;
+    const double tiny = 2.2250738585072014e-308;
+    f[0] = fabs(v1) < tiny ? 0.0 : v1;
+    f[1] = fabs(v2) < tiny ? 0.0 : v2;
+    f[2] = fabs(v3) < tiny ? 0.0 : v3;
+    f[3] = fabs(v4) < tiny ? 0.0 : v4;
+  } else if (row_ok) {
+    a.bucket[gidx * kNB + slot] = 0.0;
+  }
+  if (row_ok && a.do_sample_peak) a.speak[gidx] = fmaxf(a.speak[gidx], sp);
+  if (TPF != 0 && row_ok) {
+    a.tpeak[gidx] = fmaxf(a.tpeak[gidx], tp);
+#pragma unroll
+    for (int t = 0; t < TPW; t++) a.tphist[gidx * kTpHist + t] = w[t];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_loudness_rows_any: the serial kernel for any channel count 3..32 (5.1 at 96 kHz is BASELINE config 5).
+// Frames of C channels do not align with 16-byte quads, so each lane reads its samples one float at a time
+// from the swizzled tile; a warp holds floor(32/C) streams (lane = row*C + channel), a CTA 8 such warps, a
+// tile 32 frames (32*C floats per stream = exactly C lines, so every C is supported).
+// ------------------------------------------------------------------------------------------------
+constexpr int kAnyF = 32;
+constexpr int kAnyWarps = 8;
+
+template <int TPF>
+__global__ void __launch_bounds__(kAnyWarps * 32 + 32, 2)
+k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileArgs a, const int C) {
+  constexpr int F = kAnyF;
+  const int RW = 32 / C;                 // streams per warp
+  const int ROWS = kAnyWarps * RW;       // streams per CTA (multiple of 8)
+  const unsigned STAGE_BYTES = (unsigned)C * ROWS * 128u;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* stages = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * 32768);  // stage <= 32 KB for every C
+  uint64_t* empty = full + kStages;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const unsigned row0 = blockIdx.x * (unsigned)ROWS;
+  const unsigned nrows = min((unsigned)ROWS, a.n_streams - row0);
+  const unsigned live_warps = (nrows + RW - 1) / RW;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], live_warps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kAnyWarps) {
+    if (lane == 0 && live_warps > 0) {
+      for (unsigned tile = 0; tile < a.n_tiles; tile++) {
+        const unsigned s = tile % kStages;
+        if (tile >= (unsigned)kStages) mbar_wait(&empty[s], ((tile / kStages) - 1) & 1);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        tma_load_3d(stages + (size_t)s * 32768, &tmap, &full[s], 0, (int)row0, (int)(tile * C));
+      }
+    }
+    return;
+  }
+  if ((unsigned)warp >= live_warps) return;
+
+  const int rr = lane / C;
+  const int c = lane - rr * C;
+  const int r = warp * RW + rr;
+  const bool lane_ok = rr < RW;                     // lanes past RW*C idle
+  const bool row_ok = lane_ok && (unsigned)r < nrows;
+  const bool live = row_ok && ((a.active_mask >> c) & 1ull);
+  const size_t gidx = ((size_t)(row0 + (lane_ok ? r : 0))) * C + (lane_ok ? c : 0);
+  const unsigned key = r & 7;
+
+  double v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+  if (live) {
+    const double* f = a.filt + gidx * 4;
+    v1 = f[0]; v2 = f[1]; v3 = f[2]; v4 = f[3];
+  }
+  unsigned slot = a.slot0;
+  double acc = (live && a.pos0 > 0) ? a.bucket[gidx * kNB + slot] : 0.0;
+  float sp = 0.f, tp = 0.f;
+  constexpr int TPW = TPF == 4 ? 11 : (TPF == 2 ? 23 : 1);
+  float w[TPW];
+#pragma unroll
+  for (int t = 0; t < TPW; t++) w[t] = (TPF != 0 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
+  unsigned pos = a.pos0;
+
+  for (unsigned tile = 0; tile < a.n_tiles; tile++) {
+    const unsigned s = tile % kStages;
+    mbar_wait_warp(&full[s], (tile / kStages) & 1);
+    const unsigned char* row_base = stages + (size_t)s * 32768 + (size_t)(lane_ok ? r : 0) * 128;
+    const unsigned to_boundary = a.s100 - pos;
+#pragma unroll 4
+    for (int f = 0; f < F; f++) {
+      const int fi = f * C + (lane_ok ? c : 0);
+      const float xf = *reinterpret_cast<const float*>(row_base + (size_t)(fi >> 5) * ROWS * 128 +
+                                                        ((((fi >> 2) & 7) ^ key) << 4) + ((fi & 3) << 2));
+      sp = fmaxf(sp, fabsf(xf));
+      if (TPF == 4) {
+#pragma unroll
+        for (int ph = 0; ph < 3; ph++) {
+          float accf = xf * a.tp4[ph][0];
+#pragma unroll
+          for (int t = 1; t < 12; t++) accf = fmaf(w[t - 1], a.tp4[ph][t], accf);
+          tp = fmaxf(tp, fabsf(accf));
+        }
+      } else if (TPF == 2) {
+        float accf = xf * a.tp2[0];
+#pragma unroll
+        for (int t = 1; t < 24; t++) accf = fmaf(w[t - 1], a.tp2[t], accf);
+        tp = fmaxf(tp, fabsf(accf));
+      }
+      if (TPF != 0) {
+#pragma unroll
+        for (int t = TPW - 1; t > 0; t--) w[t] = w[t - 1];
+        w[0] = xf;
+      }
+      SSB_FILTER_STEP(SSB_CVT(xf))
+      acc = fma(y_, y_, acc);
+      if (f + 1 == (int)to_boundary) {
+        if (live) a.bucket[gidx * kNB + slot] = acc;
+        acc = 0.0;
+        slot = (slot + 1) % kNB;
+      }
+    }
+    pos = to_boundary > (unsigned)F ? pos + F : (unsigned)F - to_boundary;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  if (live) {
+    a.bucket[gidx * kNB + slot] = acc;
+    double* f = a.filt + gidx * 4;
+    const double tiny = 2.2250738585072014e-308;
+    f[0] = fabs(v1) < tiny ? 0.0 : v1;
+    f[1] = fabs(v2) < tiny ? 0.0 : v2;
+    f[2] = fabs(v3) < tiny ? 0.0 : v3;
+    f[3] = fabs(v4) < tiny ? 0.0 : v4;
+  } else if (row_ok) {
+    a.bucket[gidx * kNB + slot] = 0.0;
+  }
+  if (row_ok && a.do_sample_peak) a.speak[gidx] = fmaxf(a.speak[gidx], sp);
+  if (TPF != 0 && row_ok) {
+    a.tpeak[gidx] = fmaxf(a.tpeak[gidx], tp);
+#pragma unroll
+    for (int t = 0; t < TPW; t++) a.tphist[gidx * kTpHist + t] = w[t];
+  }
+}
 #undef SSB_FILTER_STEP
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -514,15 +837,55 @@ cudaError_t launch_tile_c(const CUtensorMap& tmap, const TileArgs& args, unsigne
   return launch_tile_cfg<C, 256, 0>(tmap, args, n_ctas, s);
 }
 
+
+template <int C, int TPF>
+cudaError_t launch_rows_cfg(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, cudaStream_t s) {
+  auto kern = k_loudness_rows<C, TPF>;
+  const size_t smem = (size_t)kStages * (kSerialF * C / 32) * kRowsSerial * 128 + 2 * kStages * sizeof(uint64_t) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e) return e;
+  kern<<<n_ctas, kRowsSerial * C + 32, smem, s>>>(tmap, args);
+  return cudaGetLastError();
+}
+
+template <int C>
+cudaError_t launch_rows_c(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, int tpf, cudaStream_t s) {
+  if (tpf == 4) return launch_rows_cfg<C, 4>(tmap, args, n_ctas, s);
+  if (tpf == 2) return launch_rows_cfg<C, 2>(tmap, args, n_ctas, s);
+  return launch_rows_cfg<C, 0>(tmap, args, n_ctas, s);
+}
+
+
+template <int TPF>
+cudaError_t launch_any_cfg(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, int C, cudaStream_t s) {
+  auto kern = k_loudness_rows_any<TPF>;
+  const size_t smem = (size_t)kStages * 32768 + 2 * kStages * sizeof(uint64_t) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e) return e;
+  kern<<<n_ctas, kAnyWarps * 32 + 32, smem, s>>>(tmap, args, C);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 constexpr int kTileT = 4;
 constexpr int kTileFMax = 256;
-static int tile_frames() { return kTileFMax; }
+
+// stream count from which the serial many-streams kernel replaces the time-segmented one
+// (SSB_SERIAL_MIN overrides it; the tests use that to run both kernels on small batches)
+static size_t serial_min_streams() {
+  static size_t v = 0;
+  if (!v) {
+    const char* e = getenv("SSB_SERIAL_MIN");
+    v = e ? (size_t)strtoull(e, nullptr, 10) : 16384;
+    if (!v) v = 1;
+  }
+  return v;
+}
 
 bool tile_path_usable(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
                       size_t in_stride_frames) {
-  if (p.channels != 1 && p.channels != 2) return false;
+  if (p.channels < 1 || p.channels > 32) return false;       // 3..32 channels: k_loudness_rows_any
   if (st.ring) return false;                      // the ring of y is written by the generic kernel
   if (p.s100 < (unsigned)kTileFMax) return false;
   if (frames < (size_t)kTileFMax) return false;
@@ -535,10 +898,14 @@ bool tile_path_usable(const LoudParams& p, const LoudState& st, const float* d_i
 // Filters the first floor(frames / F) * F frames; returns how many frames were consumed in *consumed.
 cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
                                  size_t in_stride_frames, uint32_t pos0, uint64_t bucket0, cudaStream_t s,
-                                 uint64_t* launches, size_t* consumed) {
+                                 uint64_t* launches, size_t* consumed, int force_kernel) {
   *consumed = 0;
   const int C = p.channels;
-  const int tile_f = tile_frames();
+  // force_kernel: 0 = choose by stream count, 2 = serial rows kernel, 3 = time-segmented kernel (tests)
+  const bool any_c = C > 2;
+  const bool serial = any_c || force_kernel == 2 || (force_kernel != 3 && st.n_streams >= serial_min_streams());
+  const int tile_f = any_c ? kAnyF : (serial ? kSerialF : kTileFMax);
+  const int box_rows = any_c ? kAnyWarps * (32 / C) : (serial ? kRowsSerial : kRows);
   const size_t n_tiles = frames / tile_f;
   if (!n_tiles) return cudaSuccess;
   const size_t row_floats = in_stride_frames * C;
@@ -548,17 +915,17 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   // dim1 = stream (row pitch), dim2 = line index along the row
   cuuint64_t gdim[3] = {32, (cuuint64_t)st.n_streams, (cuuint64_t)(used_floats / 32)};
   cuuint64_t gstride[2] = {(cuuint64_t)(row_floats * sizeof(float)), 128};
-  cuuint32_t box[3] = {32, (cuuint32_t)kRows, (cuuint32_t)(tile_f * C / 32)};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)(tile_f * C / 32)};
   cuuint32_t estride[3] = {1, 1, 1};
   CUresult cr = encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d_in), gdim, gstride, box,
                             estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
-  TileArgs a;
+  TileArgs a{};
   for (int i = 0; i < 5; i++) a.na[i] = -p.a[i];
   memcpy(a.b, p.b, sizeof(a.b));
-  handoff_matrix(p.a, tile_f / kTileT, a.P);
+  if (!serial) handoff_matrix(p.a, tile_f / kTileT, a.P);
   a.in = d_in;
   a.filt = st.filt;
   a.bucket = st.bucket;
@@ -579,10 +946,20 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  size_t n_ctas = (st.n_streams + kRows - 1) / kRows;
-  if (n_ctas < (size_t)sms && st.n_streams >= (size_t)sms) n_ctas = sms;  // spread rows over every SM
   const int tpf = p.do_true_peak ? p.tp_factor : 0;
-  cudaError_t e = C == 1 ? launch_tile_c<1>(tmap, a, (unsigned)n_ctas, tpf, s) : launch_tile_c<2>(tmap, a, (unsigned)n_ctas, tpf, s);
+  cudaError_t e;
+  if (any_c) {
+    const size_t n_ctas = (st.n_streams + box_rows - 1) / box_rows;
+    e = tpf == 4 ? launch_any_cfg<4>(tmap, a, (unsigned)n_ctas, C, s)
+                 : (tpf == 2 ? launch_any_cfg<2>(tmap, a, (unsigned)n_ctas, C, s) : launch_any_cfg<0>(tmap, a, (unsigned)n_ctas, C, s));
+  } else if (serial) {
+    const size_t n_ctas = (st.n_streams + kRowsSerial - 1) / kRowsSerial;
+    e = C == 1 ? launch_rows_c<1>(tmap, a, (unsigned)n_ctas, tpf, s) : launch_rows_c<2>(tmap, a, (unsigned)n_ctas, tpf, s);
+  } else {
+    size_t n_ctas = (st.n_streams + kRows - 1) / kRows;
+    if (n_ctas < (size_t)sms && st.n_streams >= (size_t)sms) n_ctas = sms;  // spread rows over every SM
+    e = C == 1 ? launch_tile_c<1>(tmap, a, (unsigned)n_ctas, tpf, s) : launch_tile_c<2>(tmap, a, (unsigned)n_ctas, tpf, s);
+  }
   if (e) return e;
   if (launches) ++*launches;
   *consumed = n_tiles * tile_f;

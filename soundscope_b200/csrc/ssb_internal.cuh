@@ -77,7 +77,7 @@ bool tile_path_usable(const LoudParams& p, const LoudState& st, const float* d_i
                       size_t in_stride_frames);
 cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
                                  size_t in_stride_frames, uint32_t pos0, uint64_t bucket0, cudaStream_t s,
-                                 uint64_t* launches, size_t* consumed);
+                                 uint64_t* launches, size_t* consumed, int force_kernel);
 // Gating for buckets [j_first, j_last] completed by the preceding filter launch.
 cudaError_t launch_gating(const GateParams& g, const LoudState& st, uint64_t j_first, uint64_t j_last,
                           cudaStream_t s, uint64_t* launches);

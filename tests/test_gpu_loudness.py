@@ -270,7 +270,9 @@ def test_cfg2_full_size_properties(ssb, oracle, cuda):
     (2, 19200, "MODE_LOUDNESS", 48000), (1, 19200, "MODE_LOUDNESS", 48000), (2, 8192, "MODE_LOUDNESS", 48000),
     (2, 48000, "MODE_LOUDNESS", 48000), (2, 1000, "MODE_LOUDNESS", 48000), (2, 19200 + 77, "MODE_LOUDNESS", 48000),
     (2, 19200, "MODE_ALL", 48000), (1, 8192, "MODE_ALL", 44100), (2, 38400, "MODE_ALL", 96000), (1, 9600 + 3, "MODE_ALL", 96000),
-    (2, 1024, "MODE_ALL", 48000)])
+    (2, 1024, "MODE_ALL", 48000),
+    # 3..32 channels go through k_loudness_rows_any (5.1 at 96 kHz is BASELINE config 5)
+    (6, 9600, "MODE_ALL", 96000), (5, 4800 + 11, "MODE_ALL", 48000), (3, 8192, "MODE_LOUDNESS", 48000), (8, 2400, "MODE_ALL", 48000)])
 def test_tile_kernel_matches_generic_and_oracle(ssb, oracle, cuda, channels, frames, mode_name, rate):
     """The TMA-tiled, time-segmented kernel against the thread-per-channel kernel and the oracle: same bucket
     sums up to f64 re-association (asserted through LUFS and identical histograms), bit-identical sample peaks,
@@ -283,30 +285,39 @@ def test_tile_kernel_matches_generic_and_oracle(ssb, oracle, cuda, channels, fra
     fast = ssb.BatchAnalyzer(n, channels, rate, mode)
     slow = ssb.BatchAnalyzer(n, channels, rate, mode)
     slow.force_generic(True)
+    fast.force_kernel(3)                       # time-segmented tile kernel
+    rows = ssb.BatchAnalyzer(n, channels, rate, mode)
+    rows.force_kernel(2)                       # serial many-streams kernel
     ob = oracle.Batch(n, channels, rate, getattr(oracle, mode_name) | oracle.MODE_SAMPLE_PEAK)
     for k in range(5):
         sl = xd[:, k * frames:(k + 1) * frames, :].contiguous()
         fast.add_frames_device(sl)
         slow.add_frames_device(sl)
+        rows.add_frames_device(sl)
         ob.add_frames(np.ascontiguousarray(x[:, k * frames:(k + 1) * frames, :]))
     want = ob.query()
-    for h in (fast, slow):
+    for h in (fast, slow, rows):
         assert close_lu(h.loudness_global(), want["global"])
         assert close_lu(h.loudness_range(), want["range"])
         assert np.array_equal(h.sample_peak(), np.abs(x).max(axis=1).astype(np.float64))
         if mode_name == "MODE_ALL":
             assert np.all(np.abs(h.true_peak() - want["true_peak"]) <= TP_RTOL * want["true_peak"])
     if mode_name == "MODE_ALL":
-        # same taps, same f32 FMA order in both kernels -> identical true peaks
+        # same taps, same f32 FMA order in all kernels -> identical true peaks
         assert np.array_equal(fast.true_peak(), slow.true_peak())
+        assert np.array_equal(rows.true_peak(), slow.true_peak())
+    # the serial many-streams kernel runs the generic kernel's operation sequence: identical state
+    assert np.array_equal(rows.results_device().cpu().numpy(), slow.results_device().cpu().numpy(), equal_nan=True) or \
+        close_lu(rows.loudness_global(), slow.loudness_global(), 1e-12)
     if (frames * 5) % ((rate + 5) // 10) == 0:
         # serial kernel: same operation order as the oracle up to FMA contraction.  Time-segmented kernel:
         # the segment hand-off (s_k = P s_{k-1} + z) re-rounds the state once per segment; measured ~1e-11 LU.
         d = np.abs(fast.loudness_momentary() - want["momentary"])
         print("tile kernel max |dLUFS| vs oracle:", d[np.isfinite(d)].max())
-        for h, tol in ((slow, 1e-9), (fast, TILE_LU_TOL)):
+        for h, tol in ((slow, 1e-9), (rows, 1e-9), (fast, TILE_LU_TOL)):
             assert close_lu(h.loudness_momentary(), want["momentary"], tol)
             assert close_lu(h.loudness_shortterm(), want["shortterm"], tol)
     for s in (0, 150, n - 1):
+        assert np.array_equal(rows.histograms(s)[0], slow.histograms(s)[0])
         assert np.array_equal(fast.histograms(s)[0], slow.histograms(s)[0])
         assert np.array_equal(fast.histograms(s)[0], ob._per_stream_hist(s)[0])

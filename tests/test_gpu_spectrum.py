@@ -186,3 +186,25 @@ def test_mic_tick_shape(ssb, oracle, cuda):
     lb = 15 * rate - 2 ** 14
     assert_db_close(a.get_fft(mid[lb:15 * rate])[:, 1], o.get_fft(om[lb:15 * rate])[:, 1])
     assert np.array_equal(a.get_waveform(mid, 15.0), o.get_waveform(om, 15.0))
+
+
+def test_process_tick_matches_separate_calls(ssb, oracle, cuda):
+    """the fused per-tick entry against the reference's three separate calls
+    (tui.rs:1482-1552: get_fft(mid), get_fft(side), add_samples + get_shortterm_lufs) on the oracle."""
+    x = sweep_stereo(6.0, 44100)
+    a, o = ssb.Analyzer(), oracle.Analyzer()
+    mid_all, side_all = oracle.mid_side(x)
+    for pos in range(2 * 16384 + 2048, x.size, 2048 * 9):      # interleaved sample positions
+        fpos = pos // 2
+        tail = x[2 * (fpos - 16384): 2 * fpos]
+        mid, side, st, fs, ls = a.process_tick(tail, 16384)
+        assert fs == 0 and ls == 0
+        o.add_samples(x[2 * fpos - 16384: 2 * fpos])
+        assert abs(st - o.get_shortterm_lufs()) <= 1e-9
+        wm, ws = o.get_fft(mid_all[fpos - 16384:fpos]), o.get_fft(side_all[fpos - 16384:fpos])
+        assert np.array_equal(mid[:, 0], wm[:, 0])
+        assert_db_close(mid[:, 1], wm[:, 1])
+        assert_db_close(side[:, 1], ws[:, 1])
+    a.create_loudness_meter(2, 22050)   # 20 kHz above Nyquist: FFT part fails, meter part still runs
+    mid, side, st, fs, ls = a.process_tick(x[:32768], 16384)
+    assert mid is None and fs == 8 and ls == 0 and np.isfinite(st)
