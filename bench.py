@@ -286,6 +286,33 @@ def run_ours(args):
                                          "frac_of_hbm_peak": fbytes / (fms * 1e-3) / 1e9 / float(measured_peaks()[0].get("hbm_gbs", 6650.0)),
                                          "windows": nwin, "kernel_ms": fms}
             del xf, out
+            # stateless rows of SURVEY §8a: min-max waveform (a11) and mid/side (a12) over 2^27 stereo-interleaved samples
+            big = (torch.rand(1 << 27, generator=g, device=dev) * 2 - 1).contiguous()
+            for name, fn, byts in (("waveform", lambda: an.waveform_device(big, 1342.17728), big.numel() * 4 + 2 * 1342177 * 4),
+                                   ("mid_side", lambda: an.mid_side_device(big), big.numel() * 8)):
+                fn()
+                torch.cuda.synchronize()
+                a0.record()
+                for i in range(5):
+                    fn()
+                a1.record()
+                torch.cuda.synchronize()
+                t = a0.elapsed_time(a1) / 5
+                extras[name] = {"samples_per_s": big.numel() / (t * 1e-3), "algorithmic_gbs": byts / (t * 1e-3) / 1e9,
+                                "frac_of_hbm_peak": byts / (t * 1e-3) / 1e9 / float(measured_peaks()[0].get("hbm_gbs", 6650.0))}
+            del big
+            # one reference-shaped player tick (tui.rs:1482-1552) through the host-facing call: 16384-frame
+            # stereo tail -> mid/side spectra + add_samples(16384 samples) + short-term LUFS, H2D/D2H included
+            import numpy as np
+            tail = (np.random.default_rng(5).uniform(-0.5, 0.5, 32768)).astype(np.float32)
+            single = S.Analyzer(device=local)
+            single.create_loudness_meter(2, RATE)
+            for i in range(5):
+                single.process_tick(tail, 16384)
+            t0 = time.perf_counter()
+            for i in range(50):
+                single.process_tick(tail, 16384)
+            extras["process_tick_us"] = (time.perf_counter() - t0) / 50 * 1e6
         except Exception as ex:  # extras never invalidate the headline
             extras["error"] = repr(ex)
 

@@ -6,8 +6,8 @@
 //   stage 2  radix 16 inside blocks of 512        (legs 32 apart)
 //   stage 3  radix 32 on 32 contiguous points     (one thread each, no twiddles)
 // Every butterfly is done in registers; the array is touched 3 times instead of log4(M) = 7.  The array
-// lives at padded positions PAD(p) = p + p/32, which keeps all three access patterns at the two-wavefront
-// minimum for 8-byte accesses.  Results stay digit-reversed (fft_position) and are read back only at the
+// lives at padded positions PAD(p) = p + p/32 + p/512, which keeps all three access patterns and the
+// epilogue's consecutive-bin reads at the two-wavefront minimum for 8-byte accesses.  Results stay digit-reversed (fft_position) and are read back only at the
 // bins the spectrum keeps.  Twiddles W_N^e come from a two-level table: hi[e >> 6] * lo[e & 63].
 //
 // All functions are __host__ __device__ so tools/test_fft_core.cu can run them on the CPU, with the
@@ -20,7 +20,9 @@ namespace ssb {
 
 #define SSB_HD __host__ __device__ __forceinline__
 
-SSB_HD unsigned fft_pad(unsigned p) { return p + (p >> 5); }
+// one pad slot per 32 points (stage 2/3 patterns) and one more per 512 (so that X[k], X[k+1], ... — which sit
+// 512 points apart after the digit reversal — fall in different banks when the epilogue reads them)
+SSB_HD unsigned fft_pad(unsigned p) { return p + (p >> 5) + (p >> 9); }
 
 SSB_HD float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 SSB_HD float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -139,7 +141,7 @@ SSB_HD void twiddle_powers(const FftTwiddle& tw, unsigned e1, unsigned n_mask, f
 template <int R1>
 SSB_HD void fft_stage1(float2* z, unsigned M, unsigned N, const FftTwiddle& tw, unsigned j) {
   const unsigned Q = M / R1;               // multiple of 32 (M >= 1024 here)
-  const unsigned QP = Q + (Q >> 5);        // padded leg stride: PAD(j + q*Q) = PAD(j) + q*QP
+  const unsigned QP = Q + (Q >> 5) + (Q >> 9);  // padded leg stride: PAD(j + q*Q) = PAD(j) + q*QP (Q = 512)
   float2* zj = z + fft_pad(j);
   float2 x[R1];
 #pragma unroll
@@ -158,7 +160,7 @@ SSB_HD void fft_stage1(float2* z, unsigned M, unsigned N, const FftTwiddle& tw, 
 // ---- stage 2: radix 16 inside blocks of 512; butterfly t of M/16 ----
 SSB_HD void fft_stage2(float2* z, unsigned N, const FftTwiddle& tw, unsigned t) {
   const unsigned b = t >> 5, j = t & 31u;
-  float2* zb = z + (b * 528u + j);         // PAD(b*512 + j + q*32) = b*528 + j + q*33
+  float2* zb = z + (b * 529u + j);         // PAD(b*512 + j + q*32) = b*529 + j + q*33
   float2 x[16];
 #pragma unroll
   for (int q = 0; q < 16; q++) x[q] = zb[q * 33];
@@ -175,7 +177,7 @@ SSB_HD void fft_stage2(float2* z, unsigned N, const FftTwiddle& tw, unsigned t) 
 
 // ---- stage 3: radix 32 on 32 contiguous points; butterfly t of M/32 ----
 SSB_HD void fft_stage3(float2* z, unsigned t) {
-  float2* zt = z + t * 33u;               // PAD(32 t + q) = 33 t + q
+  float2* zt = z + (t * 33u + (t >> 4));  // PAD(32 t + q) = 33 t + t/16 + q
   float2 x[32];
 #pragma unroll
   for (int q = 0; q < 32; q++) x[q] = zt[q];
@@ -188,7 +190,7 @@ SSB_HD void fft_stage3(float2* z, unsigned t) {
 SSB_HD unsigned fft_position(unsigned k, unsigned r1_shift) {
   const unsigned q1 = k & ((1u << r1_shift) - 1u), k1 = k >> r1_shift;
   const unsigned q2 = k1 & 15u, q3 = k1 >> 4;
-  return q1 * 528u + q2 * 33u + q3;  // PAD(q1*512 + q2*32 + q3), q3 < 32
+  return q1 * 529u + q2 * 33u + q3;  // PAD(q1*512 + q2*32 + q3), q3 < 32
 }
 
 }  // namespace ssb

@@ -261,16 +261,26 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
     o[1] = (e_s == e_s) ? (e_s <= 0.0 ? NEG_INF : energy_to_loudness(e_s)) : NaN;
   }
 
+  // Each histogram is read once, 32 independent coalesced loads per lane kept in registers (bin = lane + 32 u),
+  // and every pass below runs on the register copy; the energies table is shared by all warps (L1).
   // --- integrated: ebur128 gated_loudness, histogram branch ---
   double integrated = NaN;
   if ((mode & SSB_MODE_I) == SSB_MODE_I) {
     const uint32_t* hb = block_hist + s * kHistBins;
+    uint32_t hreg[32];
+    double ereg[32];
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+      const int i = lane + 32 * u;
+      hreg[u] = i < kHistBins ? hb[i] : 0u;
+      ereg[u] = i < kHistBins ? energies[i] : 0.0;
+    }
     double pw = 0.0;
     unsigned long long cnt = 0;
-    for (int i = lane; i < kHistBins; i += 32) {
-      const uint32_t hgt = hb[i];
-      pw = fma((double)hgt, energies[i], pw);
-      cnt += hgt;
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+      pw = fma((double)hreg[u], ereg[u], pw);
+      cnt += hreg[u];
     }
     pw = warp_sum(pw);
     cnt = warp_sum_u64(cnt);
@@ -286,11 +296,12 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
       }
       double gp = 0.0;
       unsigned long long gc = 0;
-      for (int i = lane; i < kHistBins; i += 32) {
-        if (i < start) continue;
-        const uint32_t hgt = hb[i];
-        gp = fma((double)hgt, energies[i], gp);
-        gc += hgt;
+#pragma unroll
+      for (int u = 0; u < 32; u++) {
+        if (lane + 32 * u >= start) {
+          gp = fma((double)hreg[u], ereg[u], gp);
+          gc += hreg[u];
+        }
       }
       gp = warp_sum(gp);
       gc = warp_sum_u64(gc);
@@ -301,12 +312,19 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
   double lra = NaN;
   if ((mode & SSB_MODE_LRA) == SSB_MODE_LRA) {
     const uint32_t* hs = st_hist + s * kHistBins;
+    uint32_t hreg[32];
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+      const int i = lane + 32 * u;
+      hreg[u] = i < kHistBins ? hs[i] : 0u;
+    }
     double pw = 0.0;
     unsigned long long cnt = 0;
-    for (int i = lane; i < kHistBins; i += 32) {
-      const uint32_t hgt = hs[i];
-      pw = fma((double)hgt, energies[i], pw);
-      cnt += hgt;
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+      const int i = lane + 32 * u;
+      if (hreg[u]) pw = fma((double)hreg[u], energies[i < kHistBins ? i : 0], pw);
+      cnt += hreg[u];
     }
     pw = warp_sum(pw);
     cnt = warp_sum_u64(cnt);
@@ -320,7 +338,8 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
         if (stl_integrated > energies[index]) ++index;
       }
       unsigned long long above = 0;
-      for (int i = lane; i < kHistBins; i += 32) if (i >= index) above += hs[i];
+#pragma unroll
+      for (int u = 0; u < 32; u++) if (lane + 32 * u >= index) above += hreg[u];
       above = warp_sum_u64(above);
       if (!above) lra = 0.0;
       else if (lane == 0) {

@@ -213,8 +213,10 @@ __device__ __forceinline__ void run_stage1(float2* z, unsigned M, unsigned N, co
   for (unsigned j = threadIdx.x; j < M / R1; j += blockDim.x) fft_stage1<R1>(z, M, N, tw, j);
 }
 
-template <int LAYOUT>
-__global__ void __launch_bounds__(128, 3)
+// NT threads per CTA, MINB CTAs per SM: (192, 3) up to M = 8192 (69 KB of shared memory per window),
+// (512, 1) for M = 16384 (135 KB: one window per SM, so the CTA itself has to bring the warps)
+template <int LAYOUT, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ window,
            const float2* __restrict__ g_lo, const float2* __restrict__ g_hi, unsigned k_first, unsigned n_bins,
            float* __restrict__ db_out, unsigned planes_out, unsigned plane_off, int32_t* __restrict__ status) {
@@ -225,7 +227,7 @@ k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ w
   float2* s_hi = s_lo + 64;                                            // [N/64]
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_hi + n_hi);            // 8-byte aligned: (64 + n_hi) * 8
   int* s_flags = reinterpret_cast<int*>(bar + 1);                      // [4]
-  float2* z = reinterpret_cast<float2*>(s_flags + 4);                  // [M + M/32]
+  float2* z = reinterpret_cast<float2*>(s_flags + 4);                  // [M + M/32 + M/512]
   const unsigned w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
 
   if (tid == 0) {
@@ -248,15 +250,16 @@ k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ w
   // loads are issued in batches of U per thread before any is consumed: the window streams in with
   // U * 128 independent 8/16-byte requests in flight per CTA instead of one per thread
   if (LAYOUT == 1) {
-    constexpr int U = 8;  // N >= 1024 = U * 128
+    constexpr int U = 8;
     const float2* src = reinterpret_cast<const float2*>(in) + (size_t)w * N;
     for (unsigned base = 0; base < N; base += U * nt) {
       float2 lr[U];
       float wn[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        lr[u] = __ldg(&src[base + u * nt + tid]);
-        wn[u] = __ldg(&window[base + u * nt + tid]);
+        const unsigned n = base + u * nt + tid;
+        lr[u] = n < N ? __ldg(&src[n]) : make_float2(0.f, 0.f);
+        wn[u] = n < N ? __ldg(&window[n]) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
@@ -265,17 +268,17 @@ k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ w
         const float2 v = make_float2(__fmul_rn(wn[u], mid), __fmul_rn(wn[u], side));
         mx0 = max(mx0, __float_as_uint(v.x) & 0x7fffffffu);
         mx1 = max(mx1, __float_as_uint(v.y) & 0x7fffffffu);
-        z[fft_pad(base + u * nt + tid)] = v;
+        if (base + u * nt + tid < N) z[fft_pad(base + u * nt + tid)] = v;
       }
     }
   } else {
-    constexpr int U = 4;  // M >= 512 = U * 128
+    constexpr int U = 4;
     for (unsigned base = 0; base < M; base += U * nt) {
       float x0[U], x1[U];
       float2 wn[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const unsigned m = base + u * nt + tid;
+        const unsigned m = min(base + u * nt + tid, M - 1);  // clamped; out-of-range lanes are not stored
         if (LAYOUT == 0) {
           const float2 p = __ldg(reinterpret_cast<const float2*>(in + (size_t)w * N) + m);
           x0[u] = p.x; x1[u] = p.y;
@@ -289,8 +292,8 @@ k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ w
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const float2 v = make_float2(__fmul_rn(wn[u].x, x0[u]), __fmul_rn(wn[u].y, x1[u]));
-        mx0 = max(mx0, max(__float_as_uint(v.x), __float_as_uint(v.y)) & 0x7fffffffu);
-        z[fft_pad(base + u * nt + tid)] = v;
+        mx0 = max(mx0, max(__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu));
+        if (base + u * nt + tid < M) z[fft_pad(base + u * nt + tid)] = v;
       }
     }
   }
@@ -383,12 +386,20 @@ static cudaError_t launch_fft_layout(const FftPlan& plan, const float* d_in, siz
   const unsigned N = (unsigned)plan.n;
   const unsigned M = (LAYOUT == 1) ? N : (N >> 1);
   if (M >= 512 && plan.d_tw_lo) {
-    const size_t fsmem = (size_t)(64 + (N >> 6)) * sizeof(float2) + 8 + 16 + (size_t)(M + (M >> 5) + 1) * sizeof(float2);
-    cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-    if (fe) return fe;
-    k_fft_fast<LAYOUT><<<(unsigned)n_windows, 128, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo, plan.d_tw_hi,
-                                                               (unsigned)plan.k_first, (unsigned)plan.n_bins, d_db,
-                                                               planes_out, plane_off, d_status);
+    const size_t fsmem = (size_t)(64 + (N >> 6)) * sizeof(float2) + 8 + 16 + (size_t)(M + (M >> 5) + (M >> 9) + 1) * sizeof(float2);
+    if (M > 8192) {
+      cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+      if (fe) return fe;
+      k_fft_fast<LAYOUT, 512, 1><<<(unsigned)n_windows, 512, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo, plan.d_tw_hi,
+                                                                        (unsigned)plan.k_first, (unsigned)plan.n_bins, d_db,
+                                                                        planes_out, plane_off, d_status);
+    } else {
+      cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT, 192, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+      if (fe) return fe;
+      k_fft_fast<LAYOUT, 192, 3><<<(unsigned)n_windows, 192, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo, plan.d_tw_hi,
+                                                                        (unsigned)plan.k_first, (unsigned)plan.n_bins, d_db,
+                                                                        planes_out, plane_off, d_status);
+    }
     return cudaGetLastError();
   }
   const size_t smem = (size_t)(M ? M : 1) * sizeof(float2);

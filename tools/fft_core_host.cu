@@ -21,7 +21,7 @@ extern "C" int fft_core_host(const float* in_re_im, unsigned M, unsigned N, floa
     hi[i] = make_float2((float)cos(a), (float)-sin(a));
   }
   FftTwiddle tw{lo.data(), hi.data()};
-  std::vector<float2> z(M + M / 32 + 1);
+  std::vector<float2> z(M + M / 32 + M / 512 + 1);
   for (unsigned p = 0; p < M; p++) z[fft_pad(p)] = make_float2(in_re_im[2 * p], in_re_im[2 * p + 1]);
   const unsigned R1 = M / 512;
   for (unsigned j = 0; j < M / (R1 ? R1 : 1) && R1 > 1; j++) {
