@@ -25,6 +25,7 @@ struct ssb_analyzer {
   GateParams gp{};
   LoudState st{};
   uint64_t total_frames = 0;  // frames fed per stream since the last reset
+  uint64_t gated_upto = 0;    // buckets [0, gated_upto) have been entered into the histograms
   size_t ring_pos = 0;
 
   double* d_hist_tables = nullptr;  // energies[1000] | boundaries[1001]
@@ -109,6 +110,7 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
   memset(&lp, 0, sizeof(lp));
   kweight_coeffs(rate, lp.b, lp.a);
   for (int i = 0; i < 5; i++) lp.na[i] = -lp.a[i];
+  tile_handoff_matrix(lp.a, lp.handoff);
   lp.channels = (int)channels;
   lp.s100 = (rate + 5) / 10;
   lp.do_filter = 1;  // every mode contains M
@@ -149,6 +151,7 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
   CK(cudaMalloc(&h->d_results, n * stride * sizeof(double)));
   CK(cudaMallocHost(&h->h_results, n * stride * sizeof(double)));
   h->total_frames = 0;
+  h->gated_upto = 0;
   h->ring_pos = 0;
   h->results_valid = false;
   CK(launch_reset(st, (int)channels, h->stream, &h->launches));
@@ -184,6 +187,16 @@ int32_t ensure_scratch(ssb_analyzer* h, size_t bytes) {
   return SSB_OK;
 }
 
+// enter every completed-but-ungated bucket into the histograms (separate launch)
+int32_t flush_gating(ssb_analyzer* h) {
+  const uint64_t done = h->total_frames / h->lp.s100;
+  if (done > h->gated_upto) {
+    CK(launch_gating(h->gp, h->st, h->gated_upto, done - 1, h->stream, &h->launches));
+    h->gated_upto = done;
+  }
+  return SSB_OK;
+}
+
 // feed `frames` frames per stream from device memory laid out [stream][in_stride_frames][C]
 int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in_stride_frames) {
   const uint32_t s100 = h->lp.s100;
@@ -194,6 +207,12 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
     const uint64_t bucket0 = h->total_frames / s100;
     const size_t max_frames = (size_t)kMaxBucketsPerLaunch * s100 - pos;
     const size_t n = frames - done < max_frames ? frames - done : max_frames;
+    // Gating is lazy: completed buckets wait for the next query (k_results gates them itself) unless this launch
+    // would overwrite a ring slot that a pending bucket's 3 s window still needs (64 slots, windows reach back 29)
+    if ((h->total_frames + n) / s100 > h->gated_upto + (uint64_t)(kNB - 30)) {
+      const int32_t frc = flush_gating(h);
+      if (frc) return frc;
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (h->profiling) {
       if (h->prof_used == h->prof_events.size()) {
@@ -216,8 +235,6 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
                                  (uint32_t)(t2 % s100), t2 / s100, h->ring_pos, h->stream, &h->launches));
     }
     if (ev1) CK(cudaEventRecord(ev1, h->stream));
-    const uint64_t completed = (pos + n) / s100;
-    if (completed) CK(launch_gating(h->gp, h->st, bucket0, bucket0 + completed - 1, h->stream, &h->launches));
     h->total_frames += n;
     if (h->st.ring_frames) h->ring_pos = (h->ring_pos + n) % h->st.ring_frames;
     done += n;
@@ -229,8 +246,12 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
 int32_t refresh_results(ssb_analyzer* h) {
   if (h->results_valid) return SSB_OK;
   const int aligned = (h->total_frames % h->lp.s100) == 0;
-  CK(launch_results(h->gp, h->st, h->total_frames / h->lp.s100, aligned, h->ring_pos, h->mode, h->d_results,
-                    h->stream, &h->launches));
+  {
+    const uint64_t done = h->total_frames / h->lp.s100;
+    CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, h->d_results, h->stream, &h->launches,
+                      done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0));
+    if (done > h->gated_upto) h->gated_upto = done;
+  }
   const size_t stride = 4 + 2 * (size_t)h->channels;
   CK(cudaMemcpyAsync(h->h_results, h->d_results, h->n_streams * stride * sizeof(double), cudaMemcpyDeviceToHost,
                      h->stream));
@@ -460,6 +481,7 @@ int32_t ssb_reset(ssb_analyzer* h) {
   DeviceGuard g(h->device);
   CK(launch_reset(h->st, (int)h->channels, h->stream, &h->launches));
   h->total_frames = 0;
+  h->gated_upto = 0;
   h->ring_pos = 0;
   h->results_valid = false;
   return SSB_OK;
@@ -553,8 +575,12 @@ int32_t ssb_results_device(ssb_analyzer* h, double* d_out) {
   if (!h || !d_out) return SSB_ERR_INVALID_ARG;
   DeviceGuard g(h->device);
   const int aligned = (h->total_frames % h->lp.s100) == 0;
-  CK(launch_results(h->gp, h->st, h->total_frames / h->lp.s100, aligned, h->ring_pos, h->mode, d_out, h->stream,
-                    &h->launches));
+  {
+    const uint64_t done = h->total_frames / h->lp.s100;
+    CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, d_out, h->stream, &h->launches,
+                      done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0));
+    if (done > h->gated_upto) h->gated_upto = done;
+  }
   return SSB_OK;
 }
 
@@ -728,8 +754,12 @@ int32_t ssb_process_tick(ssb_analyzer* h, const float* tail, size_t n_fft, size_
   }
   const int aligned = (h->total_frames % h->lp.s100) == 0;
   if (!h->st.ring && !aligned) *lufs_status = *lufs_status ? *lufs_status : SSB_ERR_UNALIGNED_QUERY;
-  CK(launch_results(h->gp, h->st, h->total_frames / h->lp.s100, aligned, h->ring_pos, h->mode, h->d_results, h->stream,
-                    &h->launches));
+  {
+    const uint64_t done = h->total_frames / h->lp.s100;
+    CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, h->d_results, h->stream, &h->launches,
+                      done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0));
+    if (done > h->gated_upto) h->gated_upto = done;
+  }
   CK(cudaMemcpyAsync(h->h_results, h->d_results, stride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->results_valid = true;
@@ -887,6 +917,10 @@ int32_t ssb_filter_coeffs(const ssb_analyzer* h, double b[5], double a[5]) {
 int32_t ssb_histograms(ssb_analyzer* h, size_t stream, uint64_t block[1000], uint64_t shortterm[1000]) {
   if (!h || stream >= h->n_streams || !block || !shortterm) return SSB_ERR_INVALID_ARG;
   DeviceGuard g(h->device);
+  {
+    int32_t rc = flush_gating(h);
+    if (rc) return rc;
+  }
   std::vector<uint32_t> tmp(2 * kHistBins);
   CK(cudaMemcpyAsync(tmp.data(), h->st.block_hist + stream * kHistBins, kHistBins * sizeof(uint32_t),
                      cudaMemcpyDeviceToHost, h->stream));

@@ -144,20 +144,28 @@ __device__ __forceinline__ int find_histogram_index(const double* __restrict__ b
   return lo;
 }
 
-// channel-weighted sum of `nb` buckets ending at bucket j (ebur128 calc_gating_block: per channel
-// sum, surround channels x1.41, summed over channels in channel order)
-__device__ __forceinline__ double window_energy(const double* __restrict__ bk, const GateParams& g, uint64_t j,
-                                                int nb) {
+// channel-weighted sum of NB buckets ending at bucket j (ebur128 calc_gating_block: per channel sum oldest to
+// newest, surround channels x1.41, summed over channels in channel order).  All NB loads are issued before the
+// first add: one memory latency per channel instead of NB.
+template <int NB>
+__device__ __forceinline__ double window_energy_t(const double* __restrict__ bk, const GateParams& g, uint64_t j) {
   double sum = 0.0;
   for (int c = 0; c < g.channels; c++) {
     const float w = g.weight[c];
     if (w == 0.0f) continue;
+    double v[NB];
+#pragma unroll
+    for (int k = 0; k < NB; k++) v[k] = __ldcg(&bk[c * kNB + (int)((j - (uint64_t)(NB - 1 - k)) % kNB)]);
     double ch = 0.0;
-    for (int k = nb - 1; k >= 0; k--) ch += bk[c * kNB + (int)((j - k) % kNB)];
+#pragma unroll
+    for (int k = 0; k < NB; k++) ch += v[k];
     if (w != 1.0f) ch *= 1.41;
     sum += ch;
   }
-  return sum / (double)((uint64_t)nb * g.s100);
+  return sum / (double)((uint64_t)NB * g.s100);
+}
+__device__ __forceinline__ double window_energy(const double* __restrict__ bk, const GateParams& g, uint64_t j, int nb) {
+  return nb == 4 ? window_energy_t<4>(bk, g, j) : window_energy_t<30>(bk, g, j);
 }
 
 __global__ void __launch_bounds__(128)
@@ -233,10 +241,28 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
           const float* __restrict__ speak, const float* __restrict__ tpeak, const double* __restrict__ ring,
           size_t ring_frames, size_t ring_pos, const double* __restrict__ energies,
           const double* __restrict__ bounds, uint64_t buckets_done, int aligned, int mode,
-          double* __restrict__ out) {
+          double* __restrict__ out, uint32_t* __restrict__ block_hist_rw, uint32_t* __restrict__ st_hist_rw,
+          uint64_t gate_first, uint64_t gate_last) {
   const size_t s = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (s >= n_streams) return;
+  // buckets completed since the last gating pass are gated here first (one lane per bucket), so a step that
+  // ends in a query costs one launch less; the histogram reads below then go to L2 (__ldcg)
+  if (gate_last >= gate_first) {
+    const double* bkp = bucket + s * (size_t)g.channels * kNB;
+    for (uint64_t j = gate_first + lane; j <= gate_last; j += 32) {
+      if (g.do_i && j >= 3) {
+        const double e = window_energy(bkp, g, j, 4);
+        if (e >= bounds[0]) atomicAdd(&block_hist_rw[s * kHistBins + find_histogram_index(bounds, e)], 1u);
+      }
+      if (g.do_lra && j >= 29 && (j - 29) % 10 == 0) {
+        const double e = window_energy(bkp, g, j, 30);
+        if (e >= bounds[0]) atomicAdd(&st_hist_rw[s * kHistBins + find_histogram_index(bounds, e)], 1u);
+      }
+    }
+    __threadfence();
+    __syncwarp();
+  }
   const int C = g.channels;
   const size_t stride = 4 + 2 * (size_t)C;
   double* o = out + s * stride;
@@ -261,26 +287,27 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
     o[1] = (e_s == e_s) ? (e_s <= 0.0 ? NEG_INF : energy_to_loudness(e_s)) : NaN;
   }
 
-  // Each histogram is read once, 32 independent coalesced loads per lane kept in registers (bin = lane + 32 u),
-  // and every pass below runs on the register copy; the energies table is shared by all warps (L1).
+  // Each histogram is read once into registers, lane-major: lane l owns bins [32 l, 32 l + 32) (eight 16-byte
+  // loads from L2), so sums are per-lane loops plus one warp reduction and the LRA percentile walk is a warp
+  // scan over lane totals plus a 32-step walk in one lane's registers — no dependent global loads.
+  const int bin0 = lane * 32;
   // --- integrated: ebur128 gated_loudness, histogram branch ---
   double integrated = NaN;
   if ((mode & SSB_MODE_I) == SSB_MODE_I) {
-    const uint32_t* hb = block_hist + s * kHistBins;
+    const uint4* hb4 = reinterpret_cast<const uint4*>(block_hist + s * kHistBins) + lane * 8;
     uint32_t hreg[32];
-    double ereg[32];
 #pragma unroll
-    for (int u = 0; u < 32; u++) {
-      const int i = lane + 32 * u;
-      hreg[u] = i < kHistBins ? hb[i] : 0u;
-      ereg[u] = i < kHistBins ? energies[i] : 0.0;
+    for (int q = 0; q < 8; q++) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (bin0 + 4 * q < kHistBins) v = __ldcg(hb4 + q);   // 1000 = 31 * 32 + 8: whole quads only
+      hreg[4 * q] = v.x; hreg[4 * q + 1] = v.y; hreg[4 * q + 2] = v.z; hreg[4 * q + 3] = v.w;
     }
     double pw = 0.0;
     unsigned long long cnt = 0;
 #pragma unroll
-    for (int u = 0; u < 32; u++) {
-      pw = fma((double)hreg[u], ereg[u], pw);
-      cnt += hreg[u];
+    for (int t = 0; t < 32; t++) {
+      if (hreg[t]) pw = fma((double)hreg[t], energies[bin0 + t], pw);
+      cnt += hreg[t];
     }
     pw = warp_sum(pw);
     cnt = warp_sum_u64(cnt);
@@ -297,10 +324,10 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
       double gp = 0.0;
       unsigned long long gc = 0;
 #pragma unroll
-      for (int u = 0; u < 32; u++) {
-        if (lane + 32 * u >= start) {
-          gp = fma((double)hreg[u], ereg[u], gp);
-          gc += hreg[u];
+      for (int t = 0; t < 32; t++) {
+        if (hreg[t] && bin0 + t >= start) {
+          gp = fma((double)hreg[t], energies[bin0 + t], gp);
+          gc += hreg[t];
         }
       }
       gp = warp_sum(gp);
@@ -311,20 +338,20 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
   // --- loudness range: ebur128 loudness_range, histogram branch (EBU Tech 3342) ---
   double lra = NaN;
   if ((mode & SSB_MODE_LRA) == SSB_MODE_LRA) {
-    const uint32_t* hs = st_hist + s * kHistBins;
+    const uint4* hs4 = reinterpret_cast<const uint4*>(st_hist + s * kHistBins) + lane * 8;
     uint32_t hreg[32];
 #pragma unroll
-    for (int u = 0; u < 32; u++) {
-      const int i = lane + 32 * u;
-      hreg[u] = i < kHistBins ? hs[i] : 0u;
+    for (int q = 0; q < 8; q++) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (bin0 + 4 * q < kHistBins) v = __ldcg(hs4 + q);
+      hreg[4 * q] = v.x; hreg[4 * q + 1] = v.y; hreg[4 * q + 2] = v.z; hreg[4 * q + 3] = v.w;
     }
     double pw = 0.0;
     unsigned long long cnt = 0;
 #pragma unroll
-    for (int u = 0; u < 32; u++) {
-      const int i = lane + 32 * u;
-      if (hreg[u]) pw = fma((double)hreg[u], energies[i < kHistBins ? i : 0], pw);
-      cnt += hreg[u];
+    for (int t = 0; t < 32; t++) {
+      if (hreg[t]) pw = fma((double)hreg[t], energies[bin0 + t], pw);
+      cnt += hreg[t];
     }
     pw = warp_sum(pw);
     cnt = warp_sum_u64(cnt);
@@ -337,21 +364,41 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
         index = find_histogram_index(bounds, stl_integrated);
         if (stl_integrated > energies[index]) ++index;
       }
-      unsigned long long above = 0;
+      // lane totals above the relative gate, their exclusive prefix, and the grand total
+      unsigned long long mine = 0;
 #pragma unroll
-      for (int u = 0; u < 32; u++) if (lane + 32 * u >= index) above += hreg[u];
-      above = warp_sum_u64(above);
+      for (int t = 0; t < 32; t++) if (bin0 + t >= index) mine += hreg[t];
+      unsigned long long incl = mine;
+#pragma unroll
+      for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o2);
+        if (lane >= o2) incl += up;
+      }
+      const unsigned long long above = __shfl_sync(0xffffffffu, incl, 31);
       if (!above) lra = 0.0;
-      else if (lane == 0) {
+      else {
+        const unsigned long long excl = incl - mine;
         const unsigned long long lo = (unsigned long long)((double)(above - 1) * 0.1 + 0.5);
         const unsigned long long hi = (unsigned long long)((double)(above - 1) * 0.95 + 0.5);
-        unsigned long long run = 0;
-        int j = index;
-        while (run <= lo) run += hs[j++];
-        const double l_en = energies[j - 1];
-        while (run <= hi) run += hs[j++];
-        const double h_en = energies[j - 1];
-        lra = energy_to_loudness(h_en) - energy_to_loudness(l_en);
+        // ebur128 walks `while (size <= p) size += hist[j++]` and takes bin j-1: the first bin whose running
+        // count exceeds p.  The lane whose range (excl, incl] contains p+1 finds it in its registers.
+        int lo_bin = -1, hi_bin = -1;
+        unsigned long long run = excl;
+#pragma unroll
+        for (int t = 0; t < 32; t++) {
+          if (bin0 + t >= index) {
+            run += hreg[t];
+            if (lo_bin < 0 && run > lo && excl <= lo) lo_bin = bin0 + t;
+            if (hi_bin < 0 && run > hi && excl <= hi) hi_bin = bin0 + t;
+          }
+        }
+        // exactly one lane found each (its excl <= p < incl); max-reduce the -1s away
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+          lo_bin = max(lo_bin, __shfl_xor_sync(0xffffffffu, lo_bin, o2));
+          hi_bin = max(hi_bin, __shfl_xor_sync(0xffffffffu, hi_bin, o2));
+        }
+        lra = energy_to_loudness(energies[hi_bin]) - energy_to_loudness(energies[lo_bin]);
       }
     }
   }
@@ -368,13 +415,15 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
 }
 
 cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
-                           size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches) {
+                           size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches,
+                           uint64_t gate_first, uint64_t gate_last) {
   if (!st.n_streams) return cudaSuccess;
   const int tpb = 128;
   const size_t threads = st.n_streams * 32;
   k_results<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, s>>>(
       g, st.n_streams, st.bucket, st.block_hist, st.st_hist, st.speak, st.tpeak, st.ring, st.ring_frames,
-      ring_pos, st.hist_energies, st.hist_boundaries, buckets_done, aligned, mode, d_out);
+      ring_pos, st.hist_energies, st.hist_boundaries, buckets_done, aligned, mode, d_out, st.block_hist, st.st_hist,
+      gate_first, gate_last);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -824,8 +824,15 @@ template <int C, int F, int TPF>
 cudaError_t launch_tile_cfg(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, cudaStream_t s) {
   auto kern = k_loudness_tile<C, F, TPF>;
   const size_t smem = tile_smem_bytes<C, F>();
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e) return e;
+  static bool configured_dev[64] = {false};  // per instantiation and device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& configured = configured_dev[dev_ & 63];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    configured = true;
+  }
   kern<<<n_ctas, kRows * C * 4 + 32, smem, s>>>(tmap, args);
   return cudaGetLastError();
 }
@@ -842,8 +849,15 @@ template <int C, int TPF>
 cudaError_t launch_rows_cfg(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, cudaStream_t s) {
   auto kern = k_loudness_rows<C, TPF>;
   const size_t smem = (size_t)kStages * (kSerialF * C / 32) * kRowsSerial * 128 + 2 * kStages * sizeof(uint64_t) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e) return e;
+  static bool configured_dev[64] = {false};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& configured = configured_dev[dev_ & 63];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    configured = true;
+  }
   kern<<<n_ctas, kRowsSerial * C + 32, smem, s>>>(tmap, args);
   return cudaGetLastError();
 }
@@ -860,8 +874,15 @@ template <int TPF>
 cudaError_t launch_any_cfg(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, int C, cudaStream_t s) {
   auto kern = k_loudness_rows_any<TPF>;
   const size_t smem = (size_t)kStages * 32768 + 2 * kStages * sizeof(uint64_t) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e) return e;
+  static bool configured_dev[64] = {false};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& configured = configured_dev[dev_ & 63];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    configured = true;
+  }
   kern<<<n_ctas, kAnyWarps * 32 + 32, smem, s>>>(tmap, args, C);
   return cudaGetLastError();
 }
@@ -882,6 +903,8 @@ static size_t serial_min_streams() {
   }
   return v;
 }
+
+void tile_handoff_matrix(const double a[5], double P[16]) { handoff_matrix(a, kTileFMax / kTileT, P); }
 
 bool tile_path_usable(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
                       size_t in_stride_frames) {
@@ -925,7 +948,7 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   TileArgs a{};
   for (int i = 0; i < 5; i++) a.na[i] = -p.a[i];
   memcpy(a.b, p.b, sizeof(a.b));
-  if (!serial) handoff_matrix(p.a, tile_f / kTileT, a.P);
+  if (!serial) memcpy(a.P, p.handoff, sizeof(a.P));
   a.in = d_in;
   a.filt = st.filt;
   a.bucket = st.bucket;
@@ -942,10 +965,13 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   a.slot0 = (unsigned)(bucket0 % kNB);
   a.do_sample_peak = p.do_sample_peak;
 
-  int sms = 148;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
   const int tpf = p.do_true_peak ? p.tp_factor : 0;
   cudaError_t e;
   if (any_c) {

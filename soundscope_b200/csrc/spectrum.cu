@@ -467,16 +467,54 @@ k_waveform(const float* __restrict__ x, unsigned long long len, double spp, unsi
   }
 }
 
+// Short columns (the usual case: ~48-100 samples per column): one thread per column.  A lane walks its own
+// column front to back; neighbouring lanes own neighbouring columns, so the warp as a whole touches a
+// contiguous span whose 128-byte lines stay in L1 until every lane has used them — far more loads in flight
+// than one warp per ~100-sample column can keep.
+__global__ void __launch_bounds__(256)
+k_waveform_thread(const float* __restrict__ x, unsigned long long len, double spp, unsigned long long columns,
+                  float* __restrict__ out) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < columns;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long start = (unsigned long long)__dmul_rn((double)i, spp);
+    unsigned long long end = (unsigned long long)ceil(__dmul_rn((double)(i + 1), spp));
+    if (end > len) end = len;
+    float mn = 0.0f, mx = 0.0f;
+    if (end > start) {
+      mn = mx = x[start];
+      unsigned long long j = start + 1;
+      for (; j + 4 <= end; j += 4) {
+        const float a = x[j], b = x[j + 1], c = x[j + 2], d = x[j + 3];
+        mn = fminf(fminf(mn, a), fminf(b, fminf(c, d)));
+        mx = fmaxf(fmaxf(mx, a), fmaxf(b, fmaxf(c, d)));
+      }
+      for (; j < end; j++) {
+        const float v = x[j];
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+      }
+    }
+    out[2 * i] = mn;
+    out[2 * i + 1] = mx;
+  }
+}
+
 cudaError_t launch_waveform(const float* d_samples, size_t len, size_t window, float* d_minmax, size_t columns,
                             cudaStream_t s, uint64_t* launches) {
   if (!columns) return cudaSuccess;
   const double spp = (double)len / (double)window;
   const unsigned tpb = 256;
-  size_t warps = columns;
-  size_t blocks = (warps * 32 + tpb - 1) / tpb;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  k_waveform<<<(unsigned)blocks, tpb, 0, s>>>(d_samples, (unsigned long long)len, spp,
-                                              (unsigned long long)columns, d_minmax);
+  if (spp <= 1024.0) {
+    size_t blocks = (columns + tpb - 1) / tpb;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_waveform_thread<<<(unsigned)blocks, tpb, 0, s>>>(d_samples, (unsigned long long)len, spp,
+                                                       (unsigned long long)columns, d_minmax);
+  } else {
+    size_t blocks = (columns * 32 + tpb - 1) / tpb;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_waveform<<<(unsigned)blocks, tpb, 0, s>>>(d_samples, (unsigned long long)len, spp, (unsigned long long)columns,
+                                                d_minmax);
+  }
   if (launches) ++*launches;
   return cudaGetLastError();
 }

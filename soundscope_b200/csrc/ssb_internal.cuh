@@ -31,6 +31,7 @@ struct LoudParams {
   uint32_t s100;        // samples_in_100ms
   int do_filter, do_sample_peak, do_true_peak;
   uint64_t active_mask; // bit c set: channel c is not Channel::Unused
+  double handoff[16];   // D A^64 D: segment hand-off matrix of the time-segmented kernel (tile_handoff_matrix)
 };
 
 struct GateParams {
@@ -78,12 +79,16 @@ bool tile_path_usable(const LoudParams& p, const LoudState& st, const float* d_i
 cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
                                  size_t in_stride_frames, uint32_t pos0, uint64_t bucket0, cudaStream_t s,
                                  uint64_t* launches, size_t* consumed, int force_kernel);
+// D A^64 D for the K-weighting denominator a[] (double-double on the host, rounded once); cached in LoudParams
+void tile_handoff_matrix(const double a[5], double P[16]);
 // Gating for buckets [j_first, j_last] completed by the preceding filter launch.
 cudaError_t launch_gating(const GateParams& g, const LoudState& st, uint64_t j_first, uint64_t j_last,
                           cudaStream_t s, uint64_t* launches);
-// Per-stream scalars -> d_out[n][4+2C]; aligned != 0: the feed position is on the 100 ms grid.
+// Per-stream scalars -> d_out[n][4+2C]; aligned != 0: the feed position is on the 100 ms grid.  Buckets
+// [gate_first, gate_last] (none when gate_last < gate_first) are gated inside the same launch first.
 cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
-                           size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches);
+                           size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches,
+                           uint64_t gate_first, uint64_t gate_last);
 cudaError_t launch_reset(const LoudState& st, int channels, cudaStream_t s, uint64_t* launches);
 
 // --- kernel launchers (spectrum.cu) ------------------------------------------------------------
