@@ -313,6 +313,31 @@ def run_ours(args):
             for i in range(50):
                 single.process_tick(tail, 16384)
             extras["process_tick_us"] = (time.perf_counter() - t0) / 50 * 1e6
+            # whole-file pre-analysis (tui.rs:1229-1233): calculate_integrated_lufs on a 10 s 48 kHz stereo file
+            from tests.signals import sweep_stereo
+            whole = sweep_stereo(10.0, RATE)
+            for i in range(3):
+                single.calculate_integrated_lufs(2, whole)
+            t0 = time.perf_counter()
+            for i in range(10):
+                single.calculate_integrated_lufs(2, whole)
+            extras["integrated_lufs_10s_file_ms"] = (time.perf_counter() - t0) / 10 * 1e3
+            # many-streams regime (BASELINE config 4 per-GPU shape, scaled to 32768 streams x 400 ms): serial kernel
+            an4 = S.BatchAnalyzer(32768, CHANNELS, RATE, S.MODE_LOUDNESS, device=local)
+            x4 = make_input_device(torch, 32768, FRAMES, 4321, dev)
+            for i in range(2):
+                an4.add_frames_device(x4)
+            torch.cuda.synchronize()
+            an4.profile(True)
+            for i in range(5):
+                an4.add_frames_device(x4)
+            ms4, n4 = an4.profile_read()
+            b4 = 32768 * FRAMES * CHANNELS * 4
+            extras["many_streams_32768"] = {"samples_per_s": 32768 * FRAMES * CHANNELS / (ms4 / n4 * 1e-3),
+                                            "algorithmic_gbs": b4 / (ms4 / n4 * 1e-3) / 1e9,
+                                            "frac_of_hbm_peak": b4 / (ms4 / n4 * 1e-3) / 1e9 / float(measured_peaks()[0].get("hbm_gbs", 6650.0)),
+                                            "kernel": "k_loudness_rows (serial, one lane per stream-channel)", "kernel_ms": ms4 / n4}
+            del an4, x4
         except Exception as ex:  # extras never invalidate the headline
             extras["error"] = repr(ex)
 

@@ -181,7 +181,7 @@ int32_t ssb_profile_enable(ssb_analyzer* h, int32_t on);
 int32_t ssb_profile_read(ssb_analyzer* h, double* filter_ms, uint64_t* filter_launches);
 
 /* tests only: pick the filter kernel — 0 automatic, 1 generic (thread per channel), 2 serial many-streams
- * kernel, 3 time-segmented tile kernel */
+ * kernel, 3 time-segmented tile kernel, 4 few-streams scan kernel (generic when it does not apply) */
 int32_t ssb_debug_force_generic(ssb_analyzer* h, int32_t on);
 
 /* ---- introspection used by the tests ------------------------------------------------------ */

@@ -29,6 +29,8 @@ struct ssb_analyzer {
   size_t ring_pos = 0;
 
   double* d_hist_tables = nullptr;  // energies[1000] | boundaries[1001]
+  double* d_scan_powers = nullptr;  // Pt^m table of the scan kernel (depends on the rate)
+  ssb_analyzer* oneshot = nullptr;  // cached Mode::all() meter of calculate_integrated_lufs
   double* d_results = nullptr;
   double* h_results = nullptr;  // pinned
   bool results_valid = false;
@@ -89,8 +91,10 @@ struct DeviceGuard {
 
 void free_meter(ssb_analyzer* h) {
   cudaFree(h->st.filt); cudaFree(h->st.bucket); cudaFree(h->st.block_hist); cudaFree(h->st.st_hist);
-  cudaFree(h->st.speak); cudaFree(h->st.tpeak); cudaFree(h->st.tphist); cudaFree(h->st.ring);
+  cudaFree(h->st.speak); cudaFree(h->st.tpeak); cudaFree(h->st.tphist); cudaFree(h->st.ring); cudaFree(h->st.ring_e);
   cudaFree(h->d_results);
+  cudaFree(h->d_scan_powers);
+  h->d_scan_powers = nullptr;
   if (h->h_results) cudaFreeHost(h->h_results);
   h->st = LoudState{};
   h->d_results = nullptr;
@@ -111,6 +115,12 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
   kweight_coeffs(rate, lp.b, lp.a);
   for (int i = 0; i < 5; i++) lp.na[i] = -lp.a[i];
   tile_handoff_matrix(lp.a, lp.handoff);
+  if (channels <= 2 && h->n_streams <= 64) {
+    std::vector<double> tab(scan_power_table_doubles());
+    scan_power_table(lp.a, tab.data());
+    CK(cudaMalloc(&h->d_scan_powers, tab.size() * sizeof(double)));
+    CK(cudaMemcpy(h->d_scan_powers, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   lp.channels = (int)channels;
   lp.s100 = (rate + 5) / 10;
   lp.do_filter = 1;  // every mode contains M
@@ -136,6 +146,7 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
   CK(cudaMalloc(&st.tpeak, chains * sizeof(float)));
   CK(cudaMalloc(&st.tphist, chains * kTpHist * sizeof(float)));
   st.ring = nullptr;
+  st.ring_e = nullptr;
   st.ring_frames = 0;
   if (h->flags & SSB_FLAG_RING) {
     // ebur128: 3 s (mode S) or 400 ms of filtered samples, rounded up to a multiple of samples_in_100ms
@@ -144,6 +155,7 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
     if (rf % lp.s100) rf = rf + lp.s100 - (rf % lp.s100);
     st.ring_frames = rf;
     CK(cudaMalloc(&st.ring, n * rf * channels * sizeof(double)));
+    CK(cudaMalloc(&st.ring_e, n * 2 * sizeof(double)));
   }
   st.hist_energies = h->d_hist_tables;
   st.hist_boundaries = h->d_hist_tables + 1000;
@@ -226,7 +238,11 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
       CK(cudaEventRecord(ev0, h->stream));
     }
     size_t tiled = 0;
-    if (h->force_kernel != 1 && tile_path_usable(h->lp, h->st, d_in + done * C, n, in_stride_frames))
+    if (h->d_scan_powers && (h->force_kernel == 0 || h->force_kernel == 4) && scan_path_usable(h->lp, h->st, n)) {
+      CK(launch_loudness_scan(h->lp, h->st, h->d_scan_powers, d_in + done * C, n, in_stride_frames, pos, bucket0,
+                              h->ring_pos, h->stream, &h->launches));
+      tiled = n;
+    } else if (h->force_kernel != 1 && h->force_kernel != 4 && tile_path_usable(h->lp, h->st, d_in + done * C, n, in_stride_frames))
       CK(launch_loudness_tile(h->lp, h->st, d_in + done * C, n, in_stride_frames, pos, bucket0, h->stream,
                               &h->launches, &tiled, h->force_kernel));
     if (tiled < n) {
@@ -376,6 +392,8 @@ void ssb_analyzer_destroy(ssb_analyzer* h) {
   if (!h) return;
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->oneshot) ssb_analyzer_destroy(h->oneshot);
+  h->oneshot = nullptr;
   free_meter(h);
   cudaFree(h->d_hist_tables);
   for (int i = 0; i < 2; i++) {
@@ -589,10 +607,24 @@ int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const 
   if (!h || !out || !is_some || (!samples && len)) return SSB_ERR_INVALID_ARG;
   *is_some = 0;
   DeviceGuard g(h->device);
-  ssb_analyzer* tmp = nullptr;
-  int32_t rc = ssb_analyzer_create(&tmp, channels, h->rate, SSB_MODE_ALL, 1, h->device, 0);
-  if (rc == SSB_ERR_NOMEM) return SSB_OK;  // EbuR128::new failed -> None
-  if (rc) return fail(h, rc, "calculate_integrated_lufs: cannot create meter");
+  // The reference builds a fresh EbuR128 per call; a cached meter that is reset gives the same result without
+  // paying device allocations every time.
+  ssb_analyzer* tmp = h->oneshot;
+  int32_t rc = SSB_OK;
+  if (tmp && (tmp->channels != channels || tmp->rate != h->rate)) {
+    ssb_analyzer_destroy(tmp);
+    tmp = h->oneshot = nullptr;
+  }
+  if (!tmp) {
+    rc = ssb_analyzer_create(&tmp, channels, h->rate, SSB_MODE_ALL, 1, h->device, 0);
+    if (rc == SSB_ERR_NOMEM) return SSB_OK;  // EbuR128::new failed -> None
+    if (rc) return fail(h, rc, "calculate_integrated_lufs: cannot create meter");
+    h->oneshot = tmp;
+  } else {
+    rc = ssb_reset(tmp);
+    if (rc) return fail(h, rc, "calculate_integrated_lufs: reset failed");
+  }
+  const uint64_t launches0 = tmp->launches;
   // analyzer.rs:175: chunks(sample_rate * 2); a chunk that is not whole frames makes add_frames_f32 fail -> None
   const size_t chunk = (size_t)h->rate * 2;
   bool ok = true;
@@ -601,25 +633,22 @@ int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const 
     if (n % channels != 0) ok = false;
   }
   if (ok && len) {
-    float* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, len * sizeof(float));
-    if (e) { ssb_analyzer_destroy(tmp); return cuda_fail(h, e, "cudaMalloc"); }
-    e = cudaMemcpyAsync(d, samples, len * sizeof(float), cudaMemcpyHostToDevice, tmp->stream);
+    rc = ensure_scratch(tmp, len * sizeof(float));
+    if (rc) return fail(h, rc, "calculate_integrated_lufs: %s", tmp->err);
+    float* d = tmp->d_scratch;
+    cudaError_t e = cudaMemcpyAsync(d, samples, len * sizeof(float), cudaMemcpyHostToDevice, tmp->stream);
     for (size_t off = 0; off < len && !e && !rc; off += chunk) {
       const size_t n = len - off < chunk ? len - off : chunk;
       rc = feed_device(tmp, d + off, n / channels, n / channels);
     }
-    if (!e && !rc) e = cudaStreamSynchronize(tmp->stream);
-    cudaFree(d);
-    if (e) { ssb_analyzer_destroy(tmp); return cuda_fail(h, e, "calculate_integrated_lufs"); }
+    if (e) return cuda_fail(h, e, "calculate_integrated_lufs");
   }
   if (!rc && ok) {
     double v = 0;
     rc = ssb_loudness_global(tmp, &v);
     if (!rc) { *out = v; *is_some = 1; }
   }
-  h->launches += tmp->launches;
-  ssb_analyzer_destroy(tmp);
+  h->launches += tmp->launches - launches0;
   return rc;
 }
 

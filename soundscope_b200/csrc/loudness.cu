@@ -235,6 +235,43 @@ __device__ double ring_energy(const double* __restrict__ rg, const GateParams& g
   return sum / (double)win_frames;
 }
 
+// Momentary / short-term energies from the ring of K-weighted samples (SSB_FLAG_RING handles: few streams,
+// so one 512-thread block per stream; fixed-order tree reduction).  Window sums follow ebur128
+// calc_gating_block: per channel sum of y^2 over the last W frames ending at ring_pos, surround x1.41.
+__global__ void __launch_bounds__(512)
+k_ring_energy(const GateParams g, const double* __restrict__ ring, size_t ring_frames, size_t ring_pos, int want_s,
+              double* __restrict__ e_out /* [n][2] */) {
+  __shared__ double red[512];
+  const size_t s = blockIdx.x;
+  const double* rg = ring + s * ring_frames * g.channels;
+  for (int which = 0; which < (want_s ? 2 : 1); which++) {
+    const size_t win = (size_t)g.s100 * (which ? 30 : 4);
+    double total = 0.0;
+    for (int c = 0; c < g.channels; c++) {
+      const float w = g.weight[c];
+      if (w == 0.0f) continue;
+      double part = 0.0;
+      for (size_t i = threadIdx.x; i < win; i += blockDim.x) {
+        size_t idx = ring_pos + ring_frames - win + i;
+        if (idx >= ring_frames) idx -= ring_frames;
+        const double y = rg[idx * g.channels + c];
+        part = fma(y, y, part);
+      }
+      red[threadIdx.x] = part;
+      __syncthreads();
+      for (int o = 256; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+      }
+      double ch = red[0];
+      __syncthreads();
+      if (w != 1.0f) ch *= 1.41;
+      total += ch;
+    }
+    if (threadIdx.x == 0) e_out[s * 2 + which] = total / (double)win;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucket,
           const uint32_t* __restrict__ block_hist, const uint32_t* __restrict__ st_hist,
@@ -242,7 +279,7 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
           size_t ring_frames, size_t ring_pos, const double* __restrict__ energies,
           const double* __restrict__ bounds, uint64_t buckets_done, int aligned, int mode,
           double* __restrict__ out, uint32_t* __restrict__ block_hist_rw, uint32_t* __restrict__ st_hist_rw,
-          uint64_t gate_first, uint64_t gate_last) {
+          uint64_t gate_first, uint64_t gate_last, const double* __restrict__ ring_e) {
   const size_t s = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (s >= n_streams) return;
@@ -271,7 +308,10 @@ k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucke
 
   // --- momentary / short-term ---
   double e_m = NaN, e_s = NaN;
-  if (ring) {
+  if (ring_e) {
+    e_m = ring_e[s * 2];
+    if ((mode & SSB_MODE_S) == SSB_MODE_S) e_s = ring_e[s * 2 + 1];
+  } else if (ring) {
     const double* rg = ring + s * ring_frames * C;
     e_m = ring_energy(rg, g, ring_frames, ring_pos, (size_t)g.s100 * 4, lane);
     if ((mode & SSB_MODE_S) == SSB_MODE_S) e_s = ring_energy(rg, g, ring_frames, ring_pos, (size_t)g.s100 * 30, lane);
@@ -418,12 +458,19 @@ cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t bu
                            size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches,
                            uint64_t gate_first, uint64_t gate_last) {
   if (!st.n_streams) return cudaSuccess;
+  const double* ring_e = nullptr;
+  if (st.ring && st.ring_e) {
+    k_ring_energy<<<(unsigned)st.n_streams, 512, 0, s>>>(g, st.ring, st.ring_frames, ring_pos,
+                                                         (mode & SSB_MODE_S) == SSB_MODE_S, st.ring_e);
+    if (launches) ++*launches;
+    ring_e = st.ring_e;
+  }
   const int tpb = 128;
   const size_t threads = st.n_streams * 32;
   k_results<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, s>>>(
       g, st.n_streams, st.bucket, st.block_hist, st.st_hist, st.speak, st.tpeak, st.ring, st.ring_frames,
       ring_pos, st.hist_energies, st.hist_boundaries, buckets_done, aligned, mode, d_out, st.block_hist, st.st_hist,
-      gate_first, gate_last);
+      gate_first, gate_last, ring_e);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

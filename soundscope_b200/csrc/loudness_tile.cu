@@ -905,6 +905,7 @@ static size_t serial_min_streams() {
 }
 
 void tile_handoff_matrix(const double a[5], double P[16]) { handoff_matrix(a, kTileFMax / kTileT, P); }
+void tile_handoff_power(const double a[5], int n, double P[16]) { handoff_matrix(a, n, P); }
 
 bool tile_path_usable(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
                       size_t in_stride_frames) {

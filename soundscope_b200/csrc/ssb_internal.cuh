@@ -63,6 +63,7 @@ struct LoudState {
   float* tphist;      // [n][C][kTpHist]
   double* ring;       // [n][ring_frames][C] or nullptr
   size_t ring_frames;
+  double* ring_e;     // [n][2] scratch: momentary / short-term energies from the ring
   const double* hist_energies;    // [1000]
   const double* hist_boundaries;  // [1001]
 };
@@ -81,6 +82,16 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
                                  uint64_t* launches, size_t* consumed, int force_kernel);
 // D A^64 D for the K-weighting denominator a[] (double-double on the host, rounded once); cached in LoudParams
 void tile_handoff_matrix(const double a[5], double P[16]);
+// D A^n D for any n (loudness_tile.cu); the scan kernel's table holds n = 64 m, m = 0..32
+void tile_handoff_power(const double a[5], int n, double P[16]);
+// Few-streams / long-audio kernel (loudness_scan.cu): one CTA per stream, time-parallel prefix scan of the
+// filter state; mono/stereo, any chunking, optional ring.
+void scan_power_table(const double a[5], double* host_table);
+int scan_power_table_doubles();
+bool scan_path_usable(const LoudParams& p, const LoudState& st, size_t frames);
+cudaError_t launch_loudness_scan(const LoudParams& p, const LoudState& st, const double* d_powers, const float* d_in,
+                                 size_t frames, size_t in_stride_frames, uint32_t pos0, uint64_t bucket0,
+                                 size_t ring_pos, cudaStream_t s, uint64_t* launches);
 // Gating for buckets [j_first, j_last] completed by the preceding filter launch.
 cudaError_t launch_gating(const GateParams& g, const LoudState& st, uint64_t j_first, uint64_t j_last,
                           cudaStream_t s, uint64_t* launches);

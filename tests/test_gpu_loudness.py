@@ -237,7 +237,8 @@ def test_host_and_device_feeds_agree_bitwise(ssb, cuda):
     # stream independence: stream s of the batch equals a 1-stream handle fed the same slice
     s = 17
     one = ssb.BatchAnalyzer(1, ch, rate)
-    one.add_frames_device(xd[s:s + 1].contiguous())
+    for k in range(3):      # same chunking: the time-parallel kernels re-round the state at segment hand-offs
+        one.add_frames_device(xd[s:s + 1, k * 19200:(k + 1) * 19200, :].contiguous())
     assert np.array_equal(one.results_device().cpu().numpy()[0], ra[s], equal_nan=True)
 
 
@@ -321,3 +322,41 @@ def test_tile_kernel_matches_generic_and_oracle(ssb, oracle, cuda, channels, fra
         assert np.array_equal(rows.histograms(s)[0], slow.histograms(s)[0])
         assert np.array_equal(fast.histograms(s)[0], slow.histograms(s)[0])
         assert np.array_equal(fast.histograms(s)[0], ob._per_stream_hist(s)[0])
+
+
+@pytest.mark.parametrize("n,channels,rate,flags_name,chunks", [
+    (1, 2, 48000, "FLAG_RING", [8192] * 9), (1, 2, 44100, "FLAG_RING", [44100, 777, 30000, 512, 90001]),
+    (3, 1, 48000, "FLAG_RING", [19200, 5000, 100000]), (8, 2, 48000, None, [4800 * 40]),
+    (1, 2, 96000, "FLAG_RING", [96000, 12345, 600]), (2, 2, 48000, None, [48000 * 12])])
+def test_scan_kernel_few_streams(ssb, oracle, cuda, n, channels, rate, flags_name, chunks):
+    """The few-streams time-parallel scan kernel (loudness_scan.cu) against the serial kernel and the oracle:
+    arbitrary chunking (partial last segments, several sweeps), ring and bucket handles, 4x and 2x true peak."""
+    torch = cuda
+    flags = getattr(ssb, flags_name) if flags_name else 0
+    total = sum(chunks)
+    x = stream_batch(n, total, channels, seed=total % 1000 + n, rate=rate)
+    xd = torch.from_numpy(x).cuda()
+    scan = ssb.BatchAnalyzer(n, channels, rate, ssb.MODE_ALL, flags=flags)
+    scan.force_kernel(4)
+    ser = ssb.BatchAnalyzer(n, channels, rate, ssb.MODE_ALL, flags=flags)
+    ser.force_kernel(1)
+    ob = oracle.Batch(n, channels, rate, oracle.MODE_ALL)
+    off = 0
+    for c in chunks:
+        sl = xd[:, off:off + c, :].contiguous()
+        scan.add_frames_device(sl)
+        ser.add_frames_device(sl)
+        ob.add_frames(np.ascontiguousarray(x[:, off:off + c, :]))
+        off += c
+        if flags or off % ((rate + 5) // 10) == 0:
+            want = ob.query()
+            assert close_lu(scan.loudness_shortterm(), want["shortterm"], TILE_LU_TOL)
+            assert close_lu(scan.loudness_momentary(), want["momentary"], TILE_LU_TOL)
+    want = ob.query()
+    assert close_lu(scan.loudness_global(), want["global"]) and close_lu(scan.loudness_range(), want["range"])
+    assert np.array_equal(scan.sample_peak(), ser.sample_peak())
+    assert np.array_equal(scan.true_peak(), ser.true_peak())
+    assert np.all(np.abs(scan.true_peak() - want["true_peak"]) <= TP_RTOL * want["true_peak"])
+    for s in range(n):
+        assert np.array_equal(scan.histograms(s)[0], ob._per_stream_hist(s)[0])
+        assert np.array_equal(scan.histograms(s)[1], ob._per_stream_hist(s)[1])
