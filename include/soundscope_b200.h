@@ -161,6 +161,15 @@ int32_t ssb_process_tick(ssb_analyzer* h, const float* tail, size_t n_fft, size_
                          double* xy_mid, double* xy_side, size_t cap, size_t* n_points,
                          double* shortterm_lufs, int32_t* fft_status, int32_t* lufs_status);
 
+/* ---- whole-file pre-analysis in one call -------------------------------- */
+/* What tui.rs:1207-1241 (receive_audio_file) does when a file is selected, with one H2D copy:
+ *   Analyzer::get_waveform(samples, duration_s)          -> xy_out / n_points     (tui.rs:1213-1216)
+ *   create_loudness_meter(2, rate) on this handle                                  (tui.rs:1218-1222)
+ *   calculate_integrated_lufs(2, samples)                 -> integrated / is_some  (tui.rs:1229-1233)
+ * `samples` is the whole interleaved file (HOST).  The reference hard-codes 2 channels for the meter. */
+int32_t ssb_preanalyze_file(ssb_analyzer* h, const float* samples, size_t len, uint32_t rate, double duration_s,
+                            double* xy_out, size_t cap, size_t* n_points, double* integrated, int32_t* is_some);
+
 /* ---- waveform + mid/side (stateless) ------------------------------------------------------ */
 /* Analyzer::get_waveform (analyzer.rs:107-137): HOST samples -> (i, min), (i, max) pairs. */
 int32_t ssb_get_waveform(ssb_analyzer* h, const float* samples, size_t len, double waveform_window,

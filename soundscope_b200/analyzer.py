@@ -125,6 +125,18 @@ class Analyzer:
         ok = fs.value == 0
         return (mid[: n.value] if ok else None, side[: n.value] if ok else None, st.value, fs.value, ls.value)
 
+    def preanalyze_file(self, samples, rate, duration_s):
+        """File-selected pre-analysis (reference src/tui.rs:1207-1241) in one call: returns
+        (waveform [n, 2], integrated LUFS or None); the handle's meter becomes (2, rate)."""
+        a, p = _f32(samples)
+        w = duration_s * 1000.0
+        cap = 2 * (int(w) if w > 0 else 0) + 2
+        out = np.empty((cap, 2), dtype=np.float64)
+        n, v, some = C.c_size_t(0), C.c_double(0), C.c_int32(0)
+        check(self._h, lib().ssb_preanalyze_file(self._h, p, a.size, rate, float(duration_s), out.ctypes.data, cap,
+                                                  C.byref(n), C.byref(v), C.byref(some)))
+        return out[: n.value], (v.value if some.value else None)
+
     # introspection (tests)
     def filter_coeffs(self):
         b, a = np.zeros(5), np.zeros(5)

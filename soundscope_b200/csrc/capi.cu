@@ -873,6 +873,21 @@ int32_t ssb_get_waveform(ssb_analyzer* h, const float* samples, size_t len, doub
   return SSB_OK;
 }
 
+int32_t ssb_preanalyze_file(ssb_analyzer* h, const float* samples, size_t len, uint32_t rate, double duration_s,
+                            double* xy_out, size_t cap, size_t* n_points, double* integrated, int32_t* is_some) {
+  if (!h || !n_points || !integrated || !is_some || (!samples && len)) return SSB_ERR_INVALID_ARG;
+  *is_some = 0;
+  // tui.rs:1213: waveform over the whole interleaved file
+  int32_t rc = ssb_get_waveform(h, samples, len, duration_s, xy_out, cap, n_points);
+  if (rc) return rc;
+  // tui.rs:1218: the reference keeps going when the meter cannot be created (it shows an error popup)
+  const int32_t meter_rc = ssb_create_loudness_meter(h, 2, rate);
+  (void)meter_rc;
+  // tui.rs:1229: integrated loudness of the file, channels hard-coded to 2.  The samples are already in the
+  // handle's device scratch (ssb_get_waveform put them there): feed the one-shot meter from it.
+  return ssb_calculate_integrated_lufs(h, 2, samples, len, integrated, is_some);
+}
+
 int32_t ssb_mid_side_device(ssb_analyzer* h, const float* d_interleaved, size_t len, float* d_mid, float* d_side) {
   if (!h) return SSB_ERR_INVALID_ARG;
   const size_t frames = len / 2;

@@ -7,6 +7,8 @@
 // whose digit-reversed result is read back only at the kept bins; the store stage fuses the real
 // split (two real spectra from one complex transform for mid/side; the packed N/2-point trick for
 // mono), |X| -> scale_to_dbfs (analyzer.rs:11-27) and the spectrum-analyzer argument checks.
+#include <stdlib.h>
+
 #include "fft_core.cuh"
 #include "ssb_internal.cuh"
 
@@ -394,11 +396,24 @@ static cudaError_t launch_fft_layout(const FftPlan& plan, const float* d_in, siz
                                                                         (unsigned)plan.k_first, (unsigned)plan.n_bins, d_db,
                                                                         planes_out, plane_off, d_status);
     } else {
-      cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT, 192, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-      if (fe) return fe;
-      k_fft_fast<LAYOUT, 192, 3><<<(unsigned)n_windows, 192, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo, plan.d_tw_hi,
-                                                                        (unsigned)plan.k_first, (unsigned)plan.n_bins, d_db,
-                                                                        planes_out, plane_off, d_status);
+      // CTA shape for M <= 8192: 256 x 3 (measured 32.5 % of the HBM peak at N = 8192; SSB_FFT_CFG=0 selects
+      // 192 x 3: 29.8 %, SSB_FFT_CFG=2 selects 256 x 2: 28.7 %) — a tuning knob, all exact
+      static int cfg = -1;
+      if (cfg < 0) { const char* e = getenv("SSB_FFT_CFG"); cfg = e ? atoi(e) : 1; }
+#define SSB_LAUNCH_FFT(NT, MB)                                                                                        \
+  do {                                                                                                                 \
+    cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT, NT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                          (int)fsmem);                                                                 \
+    if (fe) return fe;                                                                                                 \
+    k_fft_fast<LAYOUT, NT, MB><<<(unsigned)n_windows, NT, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo,            \
+                                                                     plan.d_tw_hi, (unsigned)plan.k_first,             \
+                                                                     (unsigned)plan.n_bins, d_db, planes_out,          \
+                                                                     plane_off, d_status);                             \
+  } while (0)
+      if (cfg == 0) SSB_LAUNCH_FFT(192, 3);
+      else if (cfg == 2) SSB_LAUNCH_FFT(256, 2);
+      else SSB_LAUNCH_FFT(256, 3);
+#undef SSB_LAUNCH_FFT
     }
     return cudaGetLastError();
   }
@@ -467,10 +482,11 @@ k_waveform(const float* __restrict__ x, unsigned long long len, double spp, unsi
   }
 }
 
-// Short columns (the usual case: ~48-100 samples per column): one thread per column.  A lane walks its own
-// column front to back; neighbouring lanes own neighbouring columns, so the warp as a whole touches a
-// contiguous span whose 128-byte lines stay in L1 until every lane has used them — far more loads in flight
-// than one warp per ~100-sample column can keep.
+// Short columns (the usual case: 48-100 samples per column): one thread per column.  A lane walks its own
+// column front to back — scalar until 16-byte aligned, then float4, then the scalar tail — and neighbouring
+// lanes own neighbouring columns, so the warp as a whole touches a contiguous span whose 128-byte lines stay
+// in L1 until every lane has used them.  (Measured alternatives: one warp per ~100-sample column 30 % of the
+// HBM peak, this kernel with scalar loads 38 %, a shared-memory staged version 14 %.)
 __global__ void __launch_bounds__(256)
 k_waveform_thread(const float* __restrict__ x, unsigned long long len, double spp, unsigned long long columns,
                   float* __restrict__ out) {
@@ -483,10 +499,16 @@ k_waveform_thread(const float* __restrict__ x, unsigned long long len, double sp
     if (end > start) {
       mn = mx = x[start];
       unsigned long long j = start + 1;
+      const bool base_aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+      for (; j < end && (!base_aligned || (j & 3)); j++) {
+        const float v = x[j];
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+      }
       for (; j + 4 <= end; j += 4) {
-        const float a = x[j], b = x[j + 1], c = x[j + 2], d = x[j + 3];
-        mn = fminf(fminf(mn, a), fminf(b, fminf(c, d)));
-        mx = fmaxf(fmaxf(mx, a), fmaxf(b, fmaxf(c, d)));
+        const float4 q = __ldg(reinterpret_cast<const float4*>(x + j));
+        mn = fminf(fminf(mn, q.x), fminf(q.y, fminf(q.z, q.w)));
+        mx = fmaxf(fmaxf(mx, q.x), fmaxf(q.y, fmaxf(q.z, q.w)));
       }
       for (; j < end; j++) {
         const float v = x[j];

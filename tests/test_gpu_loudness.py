@@ -137,7 +137,7 @@ def test_add_samples_ragged_and_empty(ssb, cuda):
 
 
 @pytest.mark.parametrize("channels,rate", [(1, 48000), (2, 44100), (2, 48000), (4, 48000), (5, 48000), (6, 96000),
-                                           (2, 192000), (2, 8000), (3, 22050), (8, 48000)])
+                                           (2, 192000), (2, 8000), (3, 22050), (8, 48000), (64, 16000), (33, 48000)])
 def test_batch_parity_channels_rates(ssb, oracle, cuda, channels, rate):
     torch = cuda
     n = 24

@@ -208,3 +208,16 @@ def test_process_tick_matches_separate_calls(ssb, oracle, cuda):
     a.create_loudness_meter(2, 22050)   # 20 kHz above Nyquist: FFT part fails, meter part still runs
     mid, side, st, fs, ls = a.process_tick(x[:32768], 16384)
     assert mid is None and fs == 8 and ls == 0 and np.isfinite(st)
+
+
+def test_preanalyze_file(ssb, oracle, cuda):
+    """file-selected pre-analysis (tui.rs:1207-1241) against the oracle's three calls."""
+    x = sweep_stereo(10.0, 48000)
+    a, o = ssb.Analyzer(), oracle.Analyzer()
+    wf, integrated = a.preanalyze_file(x, 48000, 10.0)
+    o.create_loudness_meter(2, 48000)
+    assert np.array_equal(wf, o.get_waveform(x, 10.0))
+    assert abs(integrated - o.calculate_integrated_lufs(2, x)) <= 1e-4
+    assert a.sample_rate() == 48000
+    wf, integrated = a.preanalyze_file(x[:96001], 48000, 1.0)    # ragged last chunk -> None, like the reference
+    assert integrated is None and len(wf) == 2000
