@@ -161,6 +161,31 @@ __device__ __forceinline__ double widen_int(float x) {
   y_ = fma(a.b[0], v0_, y_);                     \
   v4 = v3; v3 = v2; v2 = v1; v1 = v0_;
 
+// pass 1 of the time-segmented kernel: zero-state recursion over one lane's segment (4 DFMA / sample)
+template <int C, int SEG_CHUNKS>
+__device__ __forceinline__ void pass1_segment(const unsigned char* line0, unsigned key, int c, const TileArgs& a,
+                                              double& z1, double& z2, double& z3, double& z4) {
+  constexpr int FPQ = 4 / C;
+  z1 = z2 = z3 = z4 = 0.0;
+#pragma unroll 1
+  for (int ch = 0; ch < SEG_CHUNKS; ch++) {
+    const unsigned char* line = line0 + (size_t)ch * kRows * 128;
+#pragma unroll
+    for (int qi = 0; qi < 8; qi++) {
+      const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
+#pragma unroll
+      for (int f = 0; f < FPQ; f++) {
+        const double x = SSB_CVT(pick<C>(q, f, c));
+        double t = fma(a.na[4], z4, x);
+        t = fma(a.na[3], z3, t);
+        t = fma(a.na[2], z2, t);
+        const double z0 = fma(a.na[1], z1, t);
+        z4 = z3; z3 = z2; z2 = z1; z1 = z0;
+      }
+    }
+  }
+}
+
 // C channels (1 or 2); T = 4 time segments per tile of F frames.
 // Warp w owns rows [w*RW, (w+1)*RW) of the CTA's 32-row box, RW = 8 / C; lane = k*8 + rr*C + c holds
 // (segment k, row rr, channel c).  All four segments of a chain sit in one warp, so the segment hand-off,
@@ -244,32 +269,21 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
   for (int t = 0; t < TPW; t++) hist[t] = (TPF != 0 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
   unsigned pos_tile = a.pos0;  // position of the tile start inside the bucket in progress
-  const double na1 = a.na[1], na2 = a.na[2], na3 = a.na[3], na4 = a.na[4];
 
+  // Software pipeline over tiles: while a lane runs pass 2 on tile t (throughput-bound, 10 DFMA / sample) it
+  // also runs pass 1 on tile t+1 (one dependent DFMA chain) in the same loop, so every warp carries two
+  // independent dependency chains and the zero-state pass hides in pass 2's issue gaps.
+  const size_t seg_off = ((size_t)(k * SEG_CHUNKS) * kRows + r) * 128;
+  double z1 = 0, z2 = 0, z3 = 0, z4 = 0;
+  if (a.n_tiles > 0) {
+    mbar_wait_warp(&full[0], 0);
+    pass1_segment<C, SEG_CHUNKS>(stages + seg_off, key, c, a, z1, z2, z3, z4);
+  }
   for (unsigned tile = 0; tile < a.n_tiles; tile++) {
     const unsigned s = tile % kStages;
-    mbar_wait_warp(&full[s], (tile / kStages) & 1);
-    const unsigned char* line0 = stages + (size_t)s * STAGE_BYTES + ((size_t)(k * SEG_CHUNKS) * kRows + r) * 128;
-
-    // ---- pass 1: zero-state recursion over my segment -> z (4 DFMA / sample) ----
-    double z1 = 0, z2 = 0, z3 = 0, z4 = 0;
-#pragma unroll 1
-    for (int ch = 0; ch < SEG_CHUNKS; ch++) {
-      const unsigned char* line = line0 + (size_t)ch * kRows * 128;
-#pragma unroll
-      for (int qi = 0; qi < 8; qi++) {
-        const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
-#pragma unroll
-        for (int f = 0; f < FPQ; f++) {
-          const double x = SSB_CVT(pick<C>(q, f, c));
-          double t = fma(na4, z4, x);
-          t = fma(na3, z3, t);
-          t = fma(na2, z2, t);
-          const double z0 = fma(na1, z1, t);
-          z4 = z3; z3 = z2; z2 = z1; z1 = z0;
-        }
-      }
-    }
+    const unsigned char* line0 = stages + (size_t)s * STAGE_BYTES + seg_off;
+    const bool has_next = tile + 1 < a.n_tiles;
+    const unsigned char* line1 = stages + (size_t)((tile + 1) % kStages) * STAGE_BYTES + seg_off;
     // ---- hand-off in difference coordinates: d_k = Pt d_{k-1} + D z_{k-1}, d_0 = D carry ----
     double v1, v2, v3, v4;
     {
@@ -296,41 +310,74 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     int lb = (int)to_boundary - k * LS;              // my samples [0, lb) belong to the bucket in progress
     lb = lb < 0 ? 0 : (lb > LS ? LS : lb);
     double accA = 0.0, accB = 0.0;
-    if (lb == LS || lb == 0) {
+    double n1 = 0, n2 = 0, n3 = 0, n4 = 0;           // zero-state response of my segment of the NEXT tile
+    if (has_next) mbar_wait_warp(&full[(tile + 1) % kStages], ((tile + 1) / kStages) & 1);
+    if (has_next && to_boundary >= (unsigned)F) {
+      // fused: pass 2 on tile t and pass 1 on tile t+1, sample by sample (warp-uniform branch)
       double acc = 0.0;
 #pragma unroll 1
       for (int ch = 0; ch < SEG_CHUNKS; ch++) {
         const unsigned char* line = line0 + (size_t)ch * kRows * 128;
+        const unsigned char* lnext = line1 + (size_t)ch * kRows * 128;
 #pragma unroll
         for (int qi = 0; qi < 8; qi++) {
           const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
+          const float4 qn = *reinterpret_cast<const float4*>(lnext + ((qi ^ key) << 4));
 #pragma unroll
           for (int f = 0; f < FPQ; f++) {
             const float xf = pick<C>(q, f, c);
             sp = fmaxf(sp, fabsf(xf));
             SSB_FILTER_STEP(SSB_CVT(xf))
             acc = fma(y_, y_, acc);
+            const double xn = SSB_CVT(pick<C>(qn, f, c));
+            double tn = fma(a.na[4], n4, xn);
+            tn = fma(a.na[3], n3, tn);
+            tn = fma(a.na[2], n2, tn);
+            const double n0 = fma(a.na[1], n1, tn);
+            n4 = n3; n3 = n2; n2 = n1; n1 = n0;
           }
         }
       }
-      if (lb == LS) accA = acc; else accB = acc;
+      accA = acc;
     } else {
-      int i = 0;
+      if (lb == LS || lb == 0) {
+        double acc = 0.0;
 #pragma unroll 1
-      for (int ch = 0; ch < SEG_CHUNKS; ch++) {
-        const unsigned char* line = line0 + (size_t)ch * kRows * 128;
-#pragma unroll 1
-        for (int qi = 0; qi < 8; qi++) {
-          const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
+        for (int ch = 0; ch < SEG_CHUNKS; ch++) {
+          const unsigned char* line = line0 + (size_t)ch * kRows * 128;
 #pragma unroll
-          for (int f = 0; f < FPQ; f++, i++) {
-            const float xf = pick<C>(q, f, c);
-            sp = fmaxf(sp, fabsf(xf));
-            SSB_FILTER_STEP(SSB_CVT(xf))
-            if (i < lb) accA = fma(y_, y_, accA); else accB = fma(y_, y_, accB);
+          for (int qi = 0; qi < 8; qi++) {
+            const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
+#pragma unroll
+            for (int f = 0; f < FPQ; f++) {
+              const float xf = pick<C>(q, f, c);
+              sp = fmaxf(sp, fabsf(xf));
+              SSB_FILTER_STEP(SSB_CVT(xf))
+              acc = fma(y_, y_, acc);
+            }
+          }
+        }
+        if (lb == LS) accA = acc; else accB = acc;
+      } else {
+        int i = 0;
+#pragma unroll 1
+        for (int ch = 0; ch < SEG_CHUNKS; ch++) {
+          const unsigned char* line = line0 + (size_t)ch * kRows * 128;
+#pragma unroll 1
+          for (int qi = 0; qi < 8; qi++) {
+            const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
+#pragma unroll
+            for (int f = 0; f < FPQ; f++, i++) {
+              const float xf = pick<C>(q, f, c);
+              sp = fmaxf(sp, fabsf(xf));
+              SSB_FILTER_STEP(SSB_CVT(xf))
+              if (i < lb) accA = fma(y_, y_, accA); else accB = fma(y_, y_, accB);
+            }
           }
         }
       }
+      __syncwarp();
+      if (has_next) pass1_segment<C, SEG_CHUNKS>(line1, key, c, a, n1, n2, n3, n4);
     }
     // ---- pass 3 (Mode::TRUE_PEAK): ebur128's polyphase interpolator as an f32 FIR over my segment ----
     if (TPF != 0) {
@@ -405,6 +452,7 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     }
     pos_tile += F;
     if (pos_tile >= a.s100) pos_tile -= a.s100;
+    z1 = n1; z2 = n2; z3 = n3; z4 = n4;
   }
 
   // ---------------- epilogue: state, bucket in progress, peak ----------------
