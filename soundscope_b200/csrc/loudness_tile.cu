@@ -186,6 +186,25 @@ __device__ __forceinline__ void pass1_segment(const unsigned char* line0, unsign
   }
 }
 
+// One true-peak sample: ebur128's polyphase interpolator as f32 FMAs over the register window w[t] = x[n-1-t]
+// (same tap order in every kernel, so all kernels report identical true peaks).
+#define SSB_TP_STEP(xf)                                                         \
+  if (TPF == 4) {                                                               \
+    _Pragma("unroll") for (int ph = 0; ph < 3; ph++) {                          \
+      float acc_ = (xf) * a.tp4[ph][0];                                         \
+      _Pragma("unroll") for (int t = 1; t < 12; t++) acc_ = fmaf(w[t - 1], a.tp4[ph][t], acc_); \
+      tp = fmaxf(tp, fabsf(acc_));                                              \
+    }                                                                           \
+  } else if (TPF == 2) {                                                        \
+    float acc_ = (xf) * a.tp2[0];                                               \
+    _Pragma("unroll") for (int t = 1; t < 24; t++) acc_ = fmaf(w[t - 1], a.tp2[t], acc_); \
+    tp = fmaxf(tp, fabsf(acc_));                                                \
+  }                                                                             \
+  if (TPF != 0) {                                                               \
+    _Pragma("unroll") for (int t = TPW - 1; t > 0; t--) w[t] = w[t - 1];        \
+    w[0] = (xf);                                                                \
+  }
+
 // C channels (1 or 2); T = 4 time segments per tile of F frames.
 // Warp w owns rows [w*RW, (w+1)*RW) of the CTA's 32-row box, RW = 8 / C; lane = k*8 + rr*C + c holds
 // (segment k, row rr, channel c).  All four segments of a chain sit in one warp, so the segment hand-off,
@@ -305,7 +324,22 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       if (k == 0) { v1 = c1; v2 = c2; v3 = c3; v4 = c4; }  // exact hand-over from the previous tile
     }
 
-    // ---- pass 2: full filter from the true state (10 DFMA / sample); y^2 split at the bucket boundary ----
+    // true-peak window: the TPW samples before my segment (previous segment's tail in the same tile, or, for
+    // the first segment, the previous tile's tail carried in `hist`)
+    float w[TPW];
+    if (TPF != 0) {
+      const unsigned char* row_base = stages + (size_t)s * STAGE_BYTES + (size_t)r * 128;
+#pragma unroll
+      for (int t = 0; t < TPW; t++) {
+        const int fr = k > 0 ? k * LS - 1 - t : 0;
+        const int fi = fr * C + c;
+        const float prev = *reinterpret_cast<const float*>(row_base + (size_t)(fi >> 5) * kRows * 128 +
+                                                            ((((fi >> 2) & 7) ^ key) << 4) + ((fi & 3) << 2));
+        w[t] = k > 0 ? prev : hist[t];
+      }
+    }
+    // ---- pass 2: full filter from the true state (10 DFMA / sample) with the true-peak FIR (36 or 24 FFMA /
+    //      sample) interleaved in the same loop, so FP64 and FP32 issue slots fill each other's gaps ----
     const unsigned to_boundary = a.s100 - pos_tile;  // frames of this tile before the boundary (>= F: none)
     int lb = (int)to_boundary - k * LS;              // my samples [0, lb) belong to the bucket in progress
     lb = lb < 0 ? 0 : (lb > LS ? LS : lb);
@@ -329,6 +363,7 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             sp = fmaxf(sp, fabsf(xf));
             SSB_FILTER_STEP(SSB_CVT(xf))
             acc = fma(y_, y_, acc);
+            SSB_TP_STEP(xf)
             const double xn = SSB_CVT(pick<C>(qn, f, c));
             double tn = fma(a.na[4], n4, xn);
             tn = fma(a.na[3], n3, tn);
@@ -354,6 +389,7 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
               sp = fmaxf(sp, fabsf(xf));
               SSB_FILTER_STEP(SSB_CVT(xf))
               acc = fma(y_, y_, acc);
+              SSB_TP_STEP(xf)
             }
           }
         }
@@ -372,6 +408,7 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
               sp = fmaxf(sp, fabsf(xf));
               SSB_FILTER_STEP(SSB_CVT(xf))
               if (i < lb) accA = fma(y_, y_, accA); else accB = fma(y_, y_, accB);
+              SSB_TP_STEP(xf)
             }
           }
         }
@@ -379,48 +416,7 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       __syncwarp();
       if (has_next) pass1_segment<C, SEG_CHUNKS>(line1, key, c, a, n1, n2, n3, n4);
     }
-    // ---- pass 3 (Mode::TRUE_PEAK): ebur128's polyphase interpolator as an f32 FIR over my segment ----
     if (TPF != 0) {
-      float w[TPW];  // w[t] = x[n-1-t]
-      const unsigned char* row_base = stages + (size_t)s * STAGE_BYTES + (size_t)r * 128;
-#pragma unroll
-      for (int t = 0; t < TPW; t++) {
-        // segment k > 0 finds its history in the same tile (the previous segment's tail)
-        const int fr = k > 0 ? k * LS - 1 - t : 0;
-        const int fi = fr * C + c;
-        const float prev = *reinterpret_cast<const float*>(row_base + (size_t)(fi >> 5) * kRows * 128 +
-                                                            ((((fi >> 2) & 7) ^ key) << 4) + ((fi & 3) << 2));
-        w[t] = k > 0 ? prev : hist[t];
-      }
-#pragma unroll 1
-      for (int ch = 0; ch < SEG_CHUNKS; ch++) {
-        const unsigned char* line = line0 + (size_t)ch * kRows * 128;
-#pragma unroll
-        for (int qi = 0; qi < 8; qi++) {
-          const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
-#pragma unroll
-          for (int f = 0; f < FPQ; f++) {
-            const float xf = pick<C>(q, f, c);
-            if (TPF == 4) {
-#pragma unroll
-              for (int ph = 0; ph < 3; ph++) {
-                float acc = xf * a.tp4[ph][0];
-#pragma unroll
-                for (int t = 1; t < 12; t++) acc = fmaf(w[t - 1], a.tp4[ph][t], acc);
-                tp = fmaxf(tp, fabsf(acc));
-              }
-            } else {
-              float acc = xf * a.tp2[0];
-#pragma unroll
-              for (int t = 1; t < 24; t++) acc = fmaf(w[t - 1], a.tp2[t], acc);
-              tp = fmaxf(tp, fabsf(acc));
-            }
-#pragma unroll
-            for (int t = TPW - 1; t > 0; t--) w[t] = w[t - 1];
-            w[0] = xf;
-          }
-        }
-      }
       // the last segment's tail is the history of the next tile's first segment
 #pragma unroll
       for (int t = 0; t < TPW; t++) hist[t] = __shfl_sync(0xffffffffu, w[t], (T - 1) * 8 + q8);
@@ -794,6 +790,7 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
   }
 }
 #undef SSB_FILTER_STEP
+#undef SSB_TP_STEP
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
