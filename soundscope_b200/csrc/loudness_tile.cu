@@ -41,6 +41,7 @@ struct TileArgs {
   float* tphist;       // [n][C][kTpHist]: x[n-1-t]
   float tp4[3][12];    // factor-4 interpolator phases 1..3 (tap t multiplies x[n-t])
   float tp2[24];       // factor-2 interpolator phase 1
+  float2 tp12[12];     // (phase 1, phase 2) taps of the factor-4 interpolator, paired for FFMA2
   uint64_t active_mask;
   unsigned n_streams;
   unsigned n_tiles;    // tiles of F frames in this launch
@@ -190,19 +191,23 @@ __device__ __forceinline__ void pass1_segment(const unsigned char* line0, unsign
 // (same tap order in every kernel, so all kernels report identical true peaks).
 #define SSB_TP_STEP(xf)                                                         \
   if (TPF == 4) {                                                               \
-    _Pragma("unroll") for (int ph = 0; ph < 3; ph++) {                          \
-      float acc_ = (xf) * a.tp4[ph][0];                                         \
-      _Pragma("unroll") for (int t = 1; t < 12; t++) acc_ = fmaf(w[t - 1], a.tp4[ph][t], acc_); \
-      tp = fmaxf(tp, fabsf(acc_));                                              \
+    /* phases 1 and 2 as one packed FFMA2 per tap (two IEEE FMAs, same order as the scalar kernels), phase 3 scalar */ \
+    const float2 xx_ = make_float2((xf), (xf));                                 \
+    float2 acc12_ = make_float2((xf) * a.tp12[0].x, (xf) * a.tp12[0].y);        \
+    float acc3_ = (xf) * a.tp4[2][0];                                           \
+    _Pragma("unroll") for (int t = 1; t < 12; t++) {                            \
+      acc12_ = __ffma2_rn(w2[t - 1], a.tp12[t], acc12_);                        \
+      acc3_ = fmaf(w2[t - 1].x, a.tp4[2][t], acc3_);                            \
     }                                                                           \
+    tp = fmaxf(tp, fmaxf(fabsf(acc12_.x), fmaxf(fabsf(acc12_.y), fabsf(acc3_)))); \
+    _Pragma("unroll") for (int t = TPW - 1; t > 0; t--) w2[t] = w2[t - 1];      \
+    w2[0] = xx_;                                                                \
   } else if (TPF == 2) {                                                        \
     float acc_ = (xf) * a.tp2[0];                                               \
-    _Pragma("unroll") for (int t = 1; t < 24; t++) acc_ = fmaf(w[t - 1], a.tp2[t], acc_); \
+    _Pragma("unroll") for (int t = 1; t < 24; t++) acc_ = fmaf(w2[t - 1].x, a.tp2[t], acc_); \
     tp = fmaxf(tp, fabsf(acc_));                                                \
-  }                                                                             \
-  if (TPF != 0) {                                                               \
-    _Pragma("unroll") for (int t = TPW - 1; t > 0; t--) w[t] = w[t - 1];        \
-    w[0] = (xf);                                                                \
+    _Pragma("unroll") for (int t = TPW - 1; t > 0; t--) w2[t] = w2[t - 1];      \
+    w2[0] = make_float2((xf), (xf));                                            \
   }
 
 // C channels (1 or 2); T = 4 time segments per tile of F frames.
@@ -326,7 +331,7 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 
     // true-peak window: the TPW samples before my segment (previous segment's tail in the same tile, or, for
     // the first segment, the previous tile's tail carried in `hist`)
-    float w[TPW];
+    float2 w2[TPW];  // w2[t] = (x[n-1-t], x[n-1-t]): both halves equal so a tap feeds two phases in one FFMA2
     if (TPF != 0) {
       const unsigned char* row_base = stages + (size_t)s * STAGE_BYTES + (size_t)r * 128;
 #pragma unroll
@@ -335,7 +340,8 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const int fi = fr * C + c;
         const float prev = *reinterpret_cast<const float*>(row_base + (size_t)(fi >> 5) * kRows * 128 +
                                                             ((((fi >> 2) & 7) ^ key) << 4) + ((fi & 3) << 2));
-        w[t] = k > 0 ? prev : hist[t];
+        const float wv = k > 0 ? prev : hist[t];
+        w2[t] = make_float2(wv, wv);
       }
     }
     // ---- pass 2: full filter from the true state (10 DFMA / sample) with the true-peak FIR (36 or 24 FFMA /
@@ -419,7 +425,7 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     if (TPF != 0) {
       // the last segment's tail is the history of the next tile's first segment
 #pragma unroll
-      for (int t = 0; t < TPW; t++) hist[t] = __shfl_sync(0xffffffffu, w[t], (T - 1) * 8 + q8);
+      for (int t = 0; t < TPW; t++) hist[t] = __shfl_sync(0xffffffffu, w2[t].x, (T - 1) * 8 + q8);
     }
     // this warp is done reading the stage
     __syncwarp();
@@ -548,9 +554,12 @@ k_loudness_rows(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   double acc = (live && a.pos0 > 0) ? a.bucket[gidx * kNB + slot] : 0.0;
   float sp = 0.f, tp = 0.f;
   constexpr int TPW = TPF == 4 ? 11 : (TPF == 2 ? 23 : 1);
-  float w[TPW];
+  float2 w2[TPW];  // true-peak window, both halves equal (FFMA2 operand); lives in registers across tiles
 #pragma unroll
-  for (int t = 0; t < TPW; t++) w[t] = (TPF != 0 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
+  for (int t = 0; t < TPW; t++) {
+    const float wv = (TPF != 0 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
+    w2[t] = make_float2(wv, wv);
+  }
   unsigned pos = a.pos0;  // frames already in the bucket in progress
 
   for (unsigned tile = 0; tile < a.n_tiles; tile++) {
@@ -571,6 +580,7 @@ k_loudness_rows(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             sp = fmaxf(sp, fabsf(xf));
             SSB_FILTER_STEP(SSB_CVT(xf))
             acc = fma(y_, y_, acc);
+            SSB_TP_STEP(xf)
           }
         }
       }
@@ -589,6 +599,7 @@ k_loudness_rows(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             sp = fmaxf(sp, fabsf(xf));
             SSB_FILTER_STEP(SSB_CVT(xf))
             acc = fma(y_, y_, acc);
+            SSB_TP_STEP(xf)
             if (i + 1 == (int)to_boundary) {   // the bucket in progress is complete
               if (live) a.bucket[gidx * kNB + slot] = acc;
               acc = 0.0;
@@ -598,37 +609,6 @@ k_loudness_rows(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
       }
       pos = (unsigned)F - to_boundary;
-    }
-    if (TPF != 0) {
-#pragma unroll 1
-      for (int ch = 0; ch < CHUNKS; ch++) {
-        const unsigned char* line = line0 + (size_t)ch * kRowsSerial * 128;
-#pragma unroll
-        for (int qi = 0; qi < 8; qi++) {
-          const float4 q = *reinterpret_cast<const float4*>(line + ((qi ^ key) << 4));
-#pragma unroll
-          for (int f = 0; f < FPQ; f++) {
-            const float xf = pick<C>(q, f, c);
-            if (TPF == 4) {
-#pragma unroll
-              for (int ph = 0; ph < 3; ph++) {
-                float accf = xf * a.tp4[ph][0];
-#pragma unroll
-                for (int t = 1; t < 12; t++) accf = fmaf(w[t - 1], a.tp4[ph][t], accf);
-                tp = fmaxf(tp, fabsf(accf));
-              }
-            } else {
-              float accf = xf * a.tp2[0];
-#pragma unroll
-              for (int t = 1; t < 24; t++) accf = fmaf(w[t - 1], a.tp2[t], accf);
-              tp = fmaxf(tp, fabsf(accf));
-            }
-#pragma unroll
-            for (int t = TPW - 1; t > 0; t--) w[t] = w[t - 1];
-            w[0] = xf;
-          }
-        }
-      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
@@ -649,7 +629,7 @@ k_loudness_rows(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   if (TPF != 0 && row_ok) {
     a.tpeak[gidx] = fmaxf(a.tpeak[gidx], tp);
 #pragma unroll
-    for (int t = 0; t < TPW; t++) a.tphist[gidx * kTpHist + t] = w[t];
+    for (int t = 0; t < TPW; t++) a.tphist[gidx * kTpHist + t] = w2[t].x;
   }
 }
 
@@ -1003,6 +983,7 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   a.tphist = st.tphist;
   memcpy(a.tp4, p.tp4, sizeof(a.tp4));
   memcpy(a.tp2, p.tp2, sizeof(a.tp2));
+  for (int t = 0; t < 12; t++) a.tp12[t] = make_float2(p.tp4[0][t], p.tp4[1][t]);
   a.active_mask = p.do_filter ? p.active_mask : 0;
   a.n_streams = (unsigned)st.n_streams;
   a.n_tiles = (unsigned)n_tiles;
