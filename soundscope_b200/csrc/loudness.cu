@@ -135,13 +135,15 @@ cudaError_t launch_loudness_generic(const LoudParams& p, const LoudState& st, co
 // ------------------------------------------------------------------------------------------------
 // gating: block / short-term energies of the buckets completed by the last filter launch
 // ------------------------------------------------------------------------------------------------
+// ebur128 find_histogram_index: the bin i with boundaries[i] <= energy < boundaries[i+1] (clamped to 0..999).
+// The crate bisects the 1001 boundaries; the same index is reached here from a closed-form guess
+// (bins are 0.1 LU wide from -70 LUFS) corrected against the table, which replaces ten dependent loads by two.
 __device__ __forceinline__ int find_histogram_index(const double* __restrict__ bounds, double energy) {
-  int lo = 0, hi = 1000;
-  do {
-    const int mid = (lo + hi) >> 1;
-    if (energy >= bounds[mid]) lo = mid; else hi = mid;
-  } while (hi - lo != 1);
-  return lo;
+  int idx = (int)floor((10.0 * log10(energy) - 0.691 + 70.0) * 10.0);
+  idx = idx < 0 ? 0 : (idx > 999 ? 999 : idx);
+  while (idx > 0 && energy < bounds[idx]) --idx;
+  while (idx < 999 && energy >= bounds[idx + 1]) ++idx;
+  return idx;
 }
 
 // channel-weighted sum of NB buckets ending at bucket j (ebur128 calc_gating_block: per channel sum oldest to

@@ -230,7 +230,10 @@ k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ w
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_hi + n_hi);            // 8-byte aligned: (64 + n_hi) * 8
   int* s_flags = reinterpret_cast<int*>(bar + 1);                      // [4]
   float2* z = reinterpret_cast<float2*>(s_flags + 4);                  // [M + M/32 + M/512]
-  const unsigned w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  // LAYOUT 4: stereo input, one CTA per (window, plane): even CTAs transform mid, odd CTAs side, each through
+  // the packed N/2-point path; the pair reads the same 2*N floats back to back, so the second read is an L2 hit
+  const unsigned w = (LAYOUT == 4) ? (blockIdx.x >> 1) : blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  if (LAYOUT == 4) plane_off = blockIdx.x & 1u;
 
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_u32(bar)));
@@ -286,7 +289,7 @@ k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ w
           x0[u] = p.x; x1[u] = p.y;
         } else {
           const float4 p = __ldg(reinterpret_cast<const float4*>(in + (size_t)w * N * 2) + m);
-          if (LAYOUT == 2) { x0[u] = __fmul_rn(__fadd_rn(p.x, p.y), 0.5f); x1[u] = __fmul_rn(__fadd_rn(p.z, p.w), 0.5f); }
+          if (LAYOUT == 2 || (LAYOUT == 4 && plane_off == 0)) { x0[u] = __fmul_rn(__fadd_rn(p.x, p.y), 0.5f); x1[u] = __fmul_rn(__fadd_rn(p.z, p.w), 0.5f); }
           else { x0[u] = __fmul_rn(__fsub_rn(p.x, p.y), 0.5f); x1[u] = __fmul_rn(__fsub_rn(p.z, p.w), 0.5f); }
         }
         wn[u] = __ldg(reinterpret_cast<const float2*>(window) + m);
@@ -392,7 +395,7 @@ static cudaError_t launch_fft_layout(const FftPlan& plan, const float* d_in, siz
     if (M > 8192) {
       cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
       if (fe) return fe;
-      k_fft_fast<LAYOUT, 512, 1><<<(unsigned)n_windows, 512, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo, plan.d_tw_hi,
+      k_fft_fast<LAYOUT, 512, 1><<<(unsigned)(LAYOUT == 4 ? 2 * n_windows : n_windows), 512, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo, plan.d_tw_hi,
                                                                         (unsigned)plan.k_first, (unsigned)plan.n_bins, d_db,
                                                                         planes_out, plane_off, d_status);
     } else {
@@ -405,7 +408,7 @@ static cudaError_t launch_fft_layout(const FftPlan& plan, const float* d_in, siz
     cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT, NT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                           (int)fsmem);                                                                 \
     if (fe) return fe;                                                                                                 \
-    k_fft_fast<LAYOUT, NT, MB><<<(unsigned)n_windows, NT, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo,            \
+    k_fft_fast<LAYOUT, NT, MB><<<(unsigned)(LAYOUT == 4 ? 2 * n_windows : n_windows), NT, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo,            \
                                                                      plan.d_tw_hi, (unsigned)plan.k_first,             \
                                                                      (unsigned)plan.n_bins, d_db, planes_out,          \
                                                                      plane_off, d_status);                             \
@@ -436,15 +439,15 @@ cudaError_t launch_fft(const FftPlan& plan, const float* d_in, int layout, size_
     if (launches) ++*launches;
     return e;
   }
-  if (plan.n <= 16384) {
+  if (plan.n <= 8192) {
     e = launch_fft_layout<1>(plan, d_in, n_windows, d_db_out, 2, 0, d_status, s);
     if (launches) ++*launches;
     return e;
   }
-  e = launch_fft_layout<2>(plan, d_in, n_windows, d_db_out, 2, 0, d_status, s);
-  if (e) return e;
-  e = launch_fft_layout<3>(plan, d_in, n_windows, d_db_out, 2, 1, d_status, s);
-  if (launches) *launches += 2;
+  // N = 16384 / 32768: one N-point complex transform needs 135+ KB of shared memory (one CTA per SM); two packed
+  // N/2-point transforms per window (mid, side) in neighbouring CTAs keep three CTAs per SM at N = 16384
+  e = launch_fft_layout<4>(plan, d_in, n_windows, d_db_out, 2, 0, d_status, s);
+  if (launches) ++*launches;
   return e;
 }
 
