@@ -34,6 +34,7 @@ struct ssb_analyzer {
   double* d_results = nullptr;
   double* h_results = nullptr;  // pinned
   bool results_valid = false;
+  bool meter_ok = false;        // false while (re)initialisation failed half-way: every meter call then fails loudly
 
   float* d_stage[2] = {nullptr, nullptr};
   size_t stage_cap = 0;  // floats per staging buffer
@@ -107,6 +108,7 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
     return fail(h, SSB_ERR_NOMEM, "EbuR128::new: channels %u outside 1..=64 (Error::NoMem)", channels);
   if (rate < 16 || rate > 2822400)
     return fail(h, SSB_ERR_NOMEM, "EbuR128::new: rate %u outside 16..=2822400 (Error::NoMem)", rate);
+  h->meter_ok = false;
   free_meter(h);
   h->channels = channels;
   h->rate = rate;
@@ -167,6 +169,7 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
   h->ring_pos = 0;
   h->results_valid = false;
   CK(launch_reset(st, (int)channels, h->stream, &h->launches));
+  h->meter_ok = true;
   return SSB_OK;
 }
 
@@ -211,6 +214,7 @@ int32_t flush_gating(ssb_analyzer* h) {
 
 // feed `frames` frames per stream from device memory laid out [stream][in_stride_frames][C]
 int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in_stride_frames) {
+  if (!h->meter_ok) return fail(h, SSB_ERR_NOMEM, "the loudness meter is not initialised (a previous create/reinit failed)");
   const uint32_t s100 = h->lp.s100;
   const size_t C = h->channels;
   size_t done = 0;
@@ -260,6 +264,7 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
 }
 
 int32_t refresh_results(ssb_analyzer* h) {
+  if (!h->meter_ok) return fail(h, SSB_ERR_NOMEM, "the loudness meter is not initialised (a previous create/reinit failed)");
   if (h->results_valid) return SSB_OK;
   const int aligned = (h->total_frames % h->lp.s100) == 0;
   {
@@ -496,6 +501,7 @@ int32_t ssb_add_samples(ssb_analyzer* h, const float* interleaved, size_t len) {
 
 int32_t ssb_reset(ssb_analyzer* h) {
   if (!h) return SSB_ERR_INVALID_ARG;
+  if (!h->meter_ok) return fail(h, SSB_ERR_NOMEM, "the loudness meter is not initialised");
   DeviceGuard g(h->device);
   CK(launch_reset(h->st, (int)h->channels, h->stream, &h->launches));
   h->total_frames = 0;
@@ -591,6 +597,7 @@ size_t ssb_result_stride(const ssb_analyzer* h) { return h ? 4 + 2 * (size_t)h->
 
 int32_t ssb_results_device(ssb_analyzer* h, double* d_out) {
   if (!h || !d_out) return SSB_ERR_INVALID_ARG;
+  if (!h->meter_ok) return fail(h, SSB_ERR_NOMEM, "the loudness meter is not initialised");
   DeviceGuard g(h->device);
   const int aligned = (h->total_frames % h->lp.s100) == 0;
   {

@@ -3,7 +3,11 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import soundscope_b200 as S
-from bench import make_input_device, N_STREAMS, FRAMES, CHANNELS, RATE
+import bench
+from bench import make_input_device, N_STREAMS, FRAMES
+bench.CHANNELS = CHANNELS = int(os.environ.get("CHANNELS", 2))
+bench.RATE = RATE = int(os.environ.get("RATE", 48000))
+FRAMES = int(os.environ.get("FRAMES", FRAMES))
 
 n = int(os.environ.get("N_STREAMS", N_STREAMS))
 mode = S.MODE_ALL if "--all" in sys.argv else S.MODE_LOUDNESS
@@ -25,5 +29,5 @@ torch.cuda.synchronize()
 ms, cnt = an.profile_read()
 step = e0.elapsed_time(e1) / K
 b = n * FRAMES * CHANNELS * 4
-print(f"SSB_TILE_F={os.environ.get('SSB_TILE_F','256')} n={n} mode={'all' if mode==S.MODE_ALL else 'loudness'}: step {step*1e3:.1f} us, filter kernel {ms/cnt*1e3:.1f} us "
+print(f"ch={CHANNELS} rate={RATE} frames={FRAMES} n={n} mode={'all' if mode==S.MODE_ALL else 'loudness'}: step {step*1e3:.1f} us, filter kernel {ms/cnt*1e3:.1f} us "
       f"-> {b/(ms/cnt*1e-3)/1e9:.0f} GB/s ({b/(ms/cnt*1e-3)/1e9/6572.9*100:.1f}% of 6572.9), {n*FRAMES*CHANNELS/(step*1e-3):.3e} samples/s")
