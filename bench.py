@@ -338,6 +338,93 @@ def run_ours(args):
                                             "frac_of_hbm_peak": b4 / (ms4 / n4 * 1e-3) / 1e9 / float(measured_peaks()[0].get("hbm_gbs", 6650.0)),
                                             "kernel": "k_loudness_rows (serial, one lane per stream-channel)", "kernel_ms": ms4 / n4}
             del an4, x4
+            hbm = float(measured_peaks()[0].get("hbm_gbs", 6650.0))
+            # BASELINE config 4's per-GPU shard: 125 000 stereo streams (10^6 over 8 GPUs), one 400 ms frame per step
+            n5 = 125000
+            x5 = torch.empty((n5, FRAMES, CHANNELS), dtype=torch.float32, device=dev)
+            for s0 in range(0, n5, 5000):  # filled in slices: the generator's f64 temporaries stay small
+                x5[s0:s0 + 5000] = make_input_device(torch, min(5000, n5 - s0), FRAMES, 777 + s0, dev)
+            an5 = S.BatchAnalyzer(n5, CHANNELS, RATE, S.MODE_LOUDNESS, device=local)
+            res5 = torch.empty((n5, an5.stride), dtype=torch.float64, device=dev)
+            for i in range(2):
+                an5.add_frames_device(x5)
+                an5.results_device(res5)
+            torch.cuda.synchronize()
+            a0.record()
+            for i in range(3):
+                an5.add_frames_device(x5)
+                an5.results_device(res5)
+            a1.record()
+            torch.cuda.synchronize()
+            t5 = a0.elapsed_time(a1) / 3
+            extras["cfg4_shard_125000_streams"] = {"samples_per_s": n5 * FRAMES * CHANNELS / (t5 * 1e-3), "step_ms": t5,
+                                                   "algorithmic_gbs": n5 * FRAMES * CHANNELS * 4 / (t5 * 1e-3) / 1e9,
+                                                   "frac_of_hbm_peak": n5 * FRAMES * CHANNELS * 4 / (t5 * 1e-3) / 1e9 / hbm,
+                                                   "realtime_streams_equiv": n5 * FRAMES / RATE / (t5 * 1e-3),
+                                                   "note": "filter + gating/results query per step, 19.2 GB resident input"}
+            del an5, x5, res5
+            # BASELINE config 5 shape: 5.1 (6-channel) 96 kHz streams, Mode::all() = K-weighting + gating + sample peak + true peak
+            # (ebur128's rate rule picks the 2x interpolator at 96 kHz); 4096 streams x 400 ms
+            n6, f6 = 4096, 38400
+            x6 = (torch.rand((n6, f6, 6), generator=g, device=dev) - 0.5).contiguous()
+            for mode_name, md in (("loudness", S.MODE_LOUDNESS), ("all", S.MODE_ALL)):
+                an6 = S.BatchAnalyzer(n6, 6, 96000, md, device=local)
+                for i in range(2):
+                    an6.add_frames_device(x6)
+                torch.cuda.synchronize()
+                an6.profile(True)
+                for i in range(3):
+                    an6.add_frames_device(x6)
+                ms6, c6 = an6.profile_read()
+                b6 = n6 * f6 * 6 * 4
+                extras["cfg5_6ch_96k_" + mode_name] = {"samples_per_s": n6 * f6 * 6 / (ms6 / c6 * 1e-3), "kernel_ms": ms6 / c6,
+                                                        "algorithmic_gbs": b6 / (ms6 / c6 * 1e-3) / 1e9,
+                                                        "frac_of_hbm_peak": b6 / (ms6 / c6 * 1e-3) / 1e9 / hbm,
+                                                        "kernel": "k_loudness_rows_any"}
+                del an6
+            del x6
+            # decoded PCM -> f32 (2 or 3 B read + 4 B written per sample), 2^28 samples
+            for fmt, bps in (("s16le", 2), ("s24le", 3)):
+                nraw = 1 << 28
+                raw = torch.randint(0, 256, (nraw * bps,), generator=g, device=dev, dtype=torch.uint8)
+                outp = torch.empty(nraw, dtype=torch.float32, device=dev)
+                an.pcm_to_f32_device(raw, fmt, out=outp)
+                torch.cuda.synchronize()
+                a0.record()
+                for i in range(5):
+                    an.pcm_to_f32_device(raw, fmt, out=outp)
+                a1.record()
+                torch.cuda.synchronize()
+                tp = a0.elapsed_time(a1) / 5
+                extras["pcm_" + fmt] = {"samples_per_s": nraw / (tp * 1e-3), "algorithmic_gbs": nraw * (bps + 4) / (tp * 1e-3) / 1e9,
+                                        "frac_of_hbm_peak": nraw * (bps + 4) / (tp * 1e-3) / 1e9 / hbm, "kernel_ms": tp}
+                del raw, outp
+            # e2e with 16-bit PCM on the wire: the cfg2 step fed as raw s16 from pinned host memory (2 B/sample over PCIe)
+            raw16 = torch.empty((N_STREAMS, FRAMES, CHANNELS), dtype=torch.int16).pin_memory()
+            raw16.copy_((xs[0].cpu() * 32767.0).round().to(torch.int16))
+            an7 = S.BatchAnalyzer(N_STREAMS, CHANNELS, RATE, S.MODE_LOUDNESS, device=local)
+            for i in range(2):
+                an7.add_frames_pcm_host(raw16.view(torch.uint8), "s16le")
+                an7.loudness_global()
+            t0 = time.perf_counter()
+            for i in range(5):
+                an7.add_frames_pcm_host(raw16.view(torch.uint8), "s16le")
+                an7.loudness_global()
+            extras["e2e_s16_pcm_samples_per_s"] = samples_per_step * 5 / (time.perf_counter() - t0)
+            del an7, raw16
+            # one microphone tick (tui.rs:1427-1480) through the host-facing call: 8 ms of new stereo audio
+            # pushed into the capture ring, then mid/side spectra (N = 16384) + 15 s waveform of mid + meter + short-term
+            ring = S.CaptureRing(30 * RATE, device=local)
+            ring.push(np.random.default_rng(6).uniform(-0.5, 0.5, 30 * RATE).astype(np.float32))
+            chunk = np.random.default_rng(7).uniform(-0.5, 0.5, 2 * 384).astype(np.float32)
+            for i in range(5):
+                ring.push(chunk)
+                single.analyze_microphone_input(ring)
+            t0 = time.perf_counter()
+            for i in range(50):
+                ring.push(chunk)
+                single.analyze_microphone_input(ring)
+            extras["mic_tick_us"] = (time.perf_counter() - t0) / 50 * 1e6
         except Exception as ex:  # extras never invalidate the headline
             extras["error"] = repr(ex)
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 1
+#define SSB_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------ */
 enum {
@@ -169,6 +169,66 @@ int32_t ssb_process_tick(ssb_analyzer* h, const float* tail, size_t n_fft, size_
  * `samples` is the whole interleaved file (HOST).  The reference hard-codes 2 channels for the meter. */
 int32_t ssb_preanalyze_file(ssb_analyzer* h, const float* samples, size_t len, uint32_t rate, double duration_s,
                             double* xy_out, size_t cap, size_t* n_points, double* integrated, int32_t* is_some);
+
+/* ---- decoded-PCM input ---------------------------------------------------- */
+/* What AudioFile::decode_file (audio_player.rs:169-267) hands the analyzer for WAV / AIFF files: symphonia's
+ * PCM decoder reads the container's interleaved integer/float samples and
+ * `SampleBuffer::<f32>::copy_interleaved_ref` (audio_player.rs:248) converts each to f32 with
+ * symphonia-core 0.5.5's `FromSample` rules (Cargo.lock:2085-2087; un-vendored, restated in
+ * oracle/capture_ref.py):  u8: (s-128)/128;  s8: s/128;  s16: s/32768;  s24: s/8388608;
+ * s32: ((s as f64)/2147483648) as f32;  f32: identity;  f64: s as f32.  Every rule is exact or a single
+ * round-to-nearest-even, so the device conversion is bit-exact.  Compressed codecs (mp3, aac, flac, vorbis,
+ * alac, adpcm) are serial bitstreams and stay on the CPU. */
+enum {
+  SSB_PCM_U8 = 0, SSB_PCM_S8 = 1,
+  SSB_PCM_S16LE = 2, SSB_PCM_S16BE = 3,
+  SSB_PCM_S24LE = 4, SSB_PCM_S24BE = 5,   /* 3 bytes per sample, packed */
+  SSB_PCM_S32LE = 6, SSB_PCM_S32BE = 7,
+  SSB_PCM_F32LE = 8, SSB_PCM_F32BE = 9,
+  SSB_PCM_F64LE = 10, SSB_PCM_F64BE = 11
+};
+/* bytes per sample of a format; 0 for an unknown one */
+size_t ssb_pcm_bytes_per_sample(int32_t format);
+/* n_samples interleaved PCM samples (HOST) -> n_samples f32 (HOST), the Vec<f32> decode_file returns */
+int32_t ssb_pcm_to_f32(ssb_analyzer* h, const void* pcm, size_t n_samples, int32_t format, float* out);
+/* same on DEVICE pointers, asynchronous on the handle's stream */
+int32_t ssb_pcm_to_f32_device(ssb_analyzer* h, const void* d_pcm, size_t n_samples, int32_t format, float* d_out);
+/* add_samples on raw PCM: n_streams slices of frames_per_stream*channels samples.  HOST form: the raw bytes
+ * cross PCIe (2 B/sample for 16-bit audio instead of 4), are converted on the device and fed to the meter. */
+int32_t ssb_add_frames_pcm(ssb_analyzer* h, const void* pcm, int32_t format, size_t frames_per_stream);
+int32_t ssb_add_frames_pcm_device(ssb_analyzer* h, const void* d_pcm, int32_t format, size_t frames_per_stream);
+
+/* ---- capture ring + one microphone tick (SURVEY.md §8(f)-4 and the live half of §8(f)-1) --------- */
+/* `RBuffer` (tui.rs:37): AllocRingBuffer<f32> of 30*rate VALUES, zero-filled (main.rs:63-65,
+ * tui.rs:1783-1786), written by the cpal input callback (audio_capture.rs:40-52) and read whole by the TUI
+ * thread every tick (tui.rs:1428, 1458).  Here the ring is pinned host memory the capture thread writes with
+ * plain stores (no CUDA call, no lock: single producer, release-published write counter) plus a device mirror
+ * that each tick tops up with only the values written since the previous tick. */
+typedef struct ssb_capture_ring ssb_capture_ring;
+int32_t ssb_capture_ring_create(ssb_capture_ring** out, size_t capacity_values, int32_t device);
+void ssb_capture_ring_destroy(ssb_capture_ring* r);
+size_t ssb_capture_ring_capacity(const ssb_capture_ring* r);
+/* total values pushed since create (monotonic) */
+uint64_t ssb_capture_ring_written(const ssb_capture_ring* r);
+/* the input callback (audio_capture.rs:40-52): is_mono == 0: `extend(data)`; is_mono != 0: the reference's
+ * up-mix `[x0, 0, x1, 0, x2, ...]` (first sample alone, every later one preceded by 0.0: 2n-1 values, so each
+ * callback flips the left/right parity of what follows — reproduced as is).  Producer thread only. */
+int32_t ssb_capture_ring_push(ssb_capture_ring* r, const float* data, size_t n, int32_t is_mono);
+/* `to_vec()`: the capacity values oldest -> newest (HOST out, cap >= capacity).  Consumer thread. */
+int32_t ssb_capture_ring_to_vec(ssb_capture_ring* r, float* out, size_t cap);
+/* analyze_microphone_input (tui.rs:1427-1480) in one call, on one snapshot of the ring:
+ *   (mid, side) = get_mid_and_side_samples(ring.to_vec())                              (tui.rs:1428-1429)
+ *   get_fft(mid[15*rate - n_fft .. 15*rate]), get_fft(side[..same..])  -> xy_mid, xy_side (tui.rs:1431-1452)
+ *   Analyzer::get_waveform(mid, waveform_window)                       -> xy_wave          (tui.rs:1456)
+ *   add_samples(ring.to_vec()[30*rate - lufs_samples .. 30*rate]); get_shortterm_lufs()    (tui.rs:1458-1479)
+ * with rate = the handle's sample rate; the reference passes n_fft = lufs_samples = 16384 and 15.0.  The meter
+ * may have any channel count (a mono device gets a mono meter fed the up-mixed values, as the reference does).
+ * Ranges the reference's slices would panic on (ring shorter than 30*rate values, n_fft > 15*rate, ...) return
+ * SSB_ERR_INVALID_ARG.  xy_wave holds wave_cap pairs; statuses as in ssb_process_tick. */
+int32_t ssb_mic_tick(ssb_analyzer* h, ssb_capture_ring* ring, size_t n_fft, size_t lufs_samples,
+                     double waveform_window, double* xy_mid, double* xy_side, size_t cap, size_t* n_points,
+                     double* xy_wave, size_t wave_cap, size_t* n_wave_points, double* shortterm_lufs,
+                     int32_t* fft_status, int32_t* lufs_status);
 
 /* ---- waveform + mid/side (stateless) ------------------------------------------------------ */
 /* Analyzer::get_waveform (analyzer.rs:107-137): HOST samples -> (i, min), (i, max) pairs. */

@@ -19,6 +19,13 @@ MODE_ALL = 0x7F
 MODE_LOUDNESS = MODE_I | MODE_LRA | MODE_HISTOGRAM  # M|S|I|LRA|HISTOGRAM, no peak detectors
 FLAG_RING = 1
 FFT_MONO, FFT_MID_SIDE = 0, 1
+# ssb_pcm_* sample formats (include/soundscope_b200.h)
+PCM_U8, PCM_S8, PCM_S16LE, PCM_S16BE, PCM_S24LE, PCM_S24BE = 0, 1, 2, 3, 4, 5
+PCM_S32LE, PCM_S32BE, PCM_F32LE, PCM_F32BE, PCM_F64LE, PCM_F64BE = 6, 7, 8, 9, 10, 11
+PCM_FORMATS = {
+    "u8": PCM_U8, "s8": PCM_S8, "s16le": PCM_S16LE, "s16be": PCM_S16BE, "s24le": PCM_S24LE, "s24be": PCM_S24BE,
+    "s32le": PCM_S32LE, "s32be": PCM_S32BE, "f32le": PCM_F32LE, "f32be": PCM_F32BE, "f64le": PCM_F64LE, "f64be": PCM_F64BE,
+}
 
 OK = 0
 ERR_NAMES = {
@@ -47,6 +54,9 @@ SYMBOLS = [
     "ssb_calculate_integrated_lufs", "ssb_get_fft", "ssb_fft_bins", "ssb_fft_axis", "ssb_fft_batch_device",
     "ssb_process_tick", "ssb_preanalyze_file", "ssb_get_waveform", "ssb_waveform_device", "ssb_mid_side", "ssb_mid_side_device", "ssb_filter_coeffs",
     "ssb_histograms", "ssb_profile_enable", "ssb_profile_read", "ssb_debug_force_generic",
+    "ssb_pcm_bytes_per_sample", "ssb_pcm_to_f32", "ssb_pcm_to_f32_device", "ssb_add_frames_pcm", "ssb_add_frames_pcm_device",
+    "ssb_capture_ring_create", "ssb_capture_ring_destroy", "ssb_capture_ring_capacity", "ssb_capture_ring_written",
+    "ssb_capture_ring_push", "ssb_capture_ring_to_vec", "ssb_mic_tick",
 ]
 
 _lib = None
@@ -111,6 +121,19 @@ def lib():
         "ssb_profile_enable": (C.c_int32, [vp, C.c_int32]),
         "ssb_debug_force_generic": (C.c_int32, [vp, C.c_int32]),
         "ssb_profile_read": (C.c_int32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+        "ssb_pcm_bytes_per_sample": (C.c_size_t, [C.c_int32]),
+        "ssb_pcm_to_f32": (C.c_int32, [vp, vp, C.c_size_t, C.c_int32, f32p]),
+        "ssb_pcm_to_f32_device": (C.c_int32, [vp, vp, C.c_size_t, C.c_int32, f32p]),
+        "ssb_add_frames_pcm": (C.c_int32, [vp, vp, C.c_int32, C.c_size_t]),
+        "ssb_add_frames_pcm_device": (C.c_int32, [vp, vp, C.c_int32, C.c_size_t]),
+        "ssb_capture_ring_create": (C.c_int32, [C.POINTER(vp), C.c_size_t, C.c_int32]),
+        "ssb_capture_ring_destroy": (None, [vp]),
+        "ssb_capture_ring_capacity": (C.c_size_t, [vp]),
+        "ssb_capture_ring_written": (C.c_uint64, [vp]),
+        "ssb_capture_ring_push": (C.c_int32, [vp, f32p, C.c_size_t, C.c_int32]),
+        "ssb_capture_ring_to_vec": (C.c_int32, [vp, f32p, C.c_size_t]),
+        "ssb_mic_tick": (C.c_int32, [vp, vp, C.c_size_t, C.c_size_t, C.c_double, f64p, f64p, C.c_size_t, szp,
+                                     f64p, C.c_size_t, szp, C.POINTER(C.c_double), i32p, i32p]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():

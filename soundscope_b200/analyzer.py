@@ -125,6 +125,38 @@ class Analyzer:
         ok = fs.value == 0
         return (mid[: n.value] if ok else None, side[: n.value] if ok else None, st.value, fs.value, ls.value)
 
+    def analyze_microphone_input(self, ring, n_fft=16384, lufs_samples=16384, waveform_window=15.0):
+        """One microphone tick (reference src/tui.rs:1427-1480) on one snapshot of `ring` (a CaptureRing):
+        mid/side spectra of mid[15*rate - n_fft .. 15*rate], the 15 s waveform of mid, add_samples of the ring's
+        last `lufs_samples` values and the short-term loudness.  Returns (mid_fft, side_fft, waveform,
+        shortterm_lufs, fft_status, lufs_status); the FFT arrays are None when get_fft would return Err."""
+        cap = n_fft // 2 + 1
+        mid = np.empty((max(cap, 1), 2), dtype=np.float64)
+        side = np.empty((max(cap, 1), 2), dtype=np.float64)
+        w = waveform_window * 1000.0
+        wave_cap = 2 * (int(w) if w > 0 else 0) + 2
+        wave = np.empty((wave_cap, 2), dtype=np.float64)
+        n, nw, st = C.c_size_t(0), C.c_size_t(0), C.c_double(0)
+        fs, ls = C.c_int32(0), C.c_int32(0)
+        check(self._h, lib().ssb_mic_tick(self._h, ring._r, n_fft, lufs_samples, float(waveform_window),
+                                          mid.ctypes.data, side.ctypes.data, cap, C.byref(n), wave.ctypes.data, wave_cap,
+                                          C.byref(nw), C.byref(st), C.byref(fs), C.byref(ls)))
+        ok = fs.value == 0
+        return (mid[: n.value] if ok else None, side[: n.value] if ok else None, wave[: nw.value], st.value,
+                fs.value, ls.value)
+
+    def add_pcm(self, raw, fmt):
+        """add_samples on raw interleaved PCM bytes (the decode_file conversion runs on the device)."""
+        from .capture import pcm_format
+        code = pcm_format(fmt)
+        b = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else np.ascontiguousarray(raw).view(np.uint8).ravel()
+        bps = lib().ssb_pcm_bytes_per_sample(code)
+        ch = lib().ssb_channels(self._h)
+        n = b.size // bps if bps else 0
+        if not bps or n % ch:
+            raise SsbError(1 if bps else 10, "ragged PCM input")
+        check(self._h, lib().ssb_add_frames_pcm(self._h, b.ctypes.data, code, n // ch))
+
     def preanalyze_file(self, samples, rate, duration_s):
         """File-selected pre-analysis (reference src/tui.rs:1207-1241) in one call: returns
         (waveform [n, 2], integrated LUFS or None); the handle's meter becomes (2, rate)."""

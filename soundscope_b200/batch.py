@@ -76,6 +76,43 @@ class BatchAnalyzer:
             ptr, frames = x.ctypes.data, x.shape[1]
         check(self._h, lib().ssb_add_frames_f32(self._h, C.c_void_p(ptr), frames))
 
+    def add_frames_pcm_device(self, raw, fmt):
+        """raw: uint8 CUDA tensor holding [n_streams, frames, channels] interleaved PCM samples of format `fmt`."""
+        from .capture import pcm_format
+        code = pcm_format(fmt)
+        bps = lib().ssb_pcm_bytes_per_sample(code)
+        assert raw.is_cuda and raw.is_contiguous() and raw.element_size() == 1
+        frames = raw.numel() // (bps * self.n_streams * self.channels)
+        assert frames * bps * self.n_streams * self.channels == raw.numel()
+        check(self._h, lib().ssb_add_frames_pcm_device(self._h, C.c_void_p(raw.data_ptr()), code, frames))
+
+    def add_frames_pcm_host(self, raw, fmt):
+        """raw: host uint8 array / pinned tensor of interleaved PCM; the raw bytes cross PCIe, conversion is on the device."""
+        from .capture import pcm_format
+        code = pcm_format(fmt)
+        bps = lib().ssb_pcm_bytes_per_sample(code)
+        if hasattr(raw, "data_ptr"):
+            ptr, nbytes = raw.data_ptr(), raw.numel() * raw.element_size()
+        else:
+            raw = np.ascontiguousarray(raw).view(np.uint8).ravel()
+            ptr, nbytes = raw.ctypes.data, raw.size
+        frames = nbytes // (bps * self.n_streams * self.channels)
+        assert frames * bps * self.n_streams * self.channels == nbytes
+        check(self._h, lib().ssb_add_frames_pcm(self._h, C.c_void_p(ptr), code, frames))
+
+    def pcm_to_f32_device(self, raw, fmt, out=None):
+        """raw: uint8 CUDA tensor of interleaved PCM -> float32 CUDA tensor (same sample order)."""
+        import torch
+        from .capture import pcm_format
+        code = pcm_format(fmt)
+        bps = lib().ssb_pcm_bytes_per_sample(code)
+        assert raw.is_cuda and raw.is_contiguous() and raw.element_size() == 1
+        n = raw.numel() // bps
+        if out is None:
+            out = torch.empty(n, dtype=torch.float32, device=raw.device)
+        check(self._h, lib().ssb_pcm_to_f32_device(self._h, C.c_void_p(raw.data_ptr()), n, code, C.c_void_p(out.data_ptr())))
+        return out
+
     def results_device(self, out=None):
         """[n_streams, 4+2C] f64 CUDA tensor: momentary, shortterm, integrated, LRA, true_peak[C], sample_peak[C]."""
         import torch

@@ -9,86 +9,14 @@
 #include <memory>
 #include <new>
 
-#include "ssb_internal.cuh"
+#include "ssb_handle.cuh"
 
 using namespace ssb;
 
-struct ssb_analyzer {
-  int device = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  uint32_t channels = 0, rate = 0;
-  int32_t mode = 0;
-  size_t n_streams = 0;
-  uint32_t flags = 0;
 
-  LoudParams lp{};
-  GateParams gp{};
-  LoudState st{};
-  uint64_t total_frames = 0;  // frames fed per stream since the last reset
-  uint64_t gated_upto = 0;    // buckets [0, gated_upto) have been entered into the histograms
-  size_t ring_pos = 0;
-
-  double* d_hist_tables = nullptr;  // energies[1000] | boundaries[1001]
-  double* d_scan_powers = nullptr;  // Pt^m table of the scan kernel (depends on the rate)
-  ssb_analyzer* oneshot = nullptr;  // cached Mode::all() meter of calculate_integrated_lufs
-  double* d_results = nullptr;
-  double* h_results = nullptr;  // pinned
-  bool results_valid = false;
-  bool meter_ok = false;        // false while (re)initialisation failed half-way: every meter call then fails loudly
-
-  float* d_stage[2] = {nullptr, nullptr};
-  size_t stage_cap = 0;  // floats per staging buffer
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
-  int stage_idx = 0;
-  float* d_scratch = nullptr;  // outputs of single-shot host calls
-  size_t scratch_cap = 0;      // bytes
-  void* h_scratch = nullptr;   // pinned mirror
-  size_t h_scratch_cap = 0;
-
-  std::map<std::pair<size_t, uint32_t>, FftPlan> plans;
-  std::map<std::pair<size_t, uint32_t>, std::pair<std::vector<double>, std::vector<double>>> axes;
-
-  uint64_t launches = 0;
-  int force_kernel = 0;  // tests: 0 auto, 1 generic kernel, 2 serial rows kernel, 3 time-segmented tile kernel
-  bool profiling = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
-  size_t prof_used = 0;
-  char err[256] = {0};
-};
+namespace ssb {
 
 namespace {
-
-int32_t fail(ssb_analyzer* h, int32_t code, const char* fmt, ...) {
-  if (h) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(h->err, sizeof(h->err), fmt, ap);
-    va_end(ap);
-  }
-  return code;
-}
-
-int32_t cuda_fail(ssb_analyzer* h, cudaError_t e, const char* what) {
-  return fail(h, SSB_ERR_CUDA + (int32_t)e, "%s: %s", what, cudaGetErrorString(e));
-}
-
-#define CK(call)                                                  \
-  do {                                                            \
-    cudaError_t e__ = (call);                                     \
-    if (e__ != cudaSuccess) return cuda_fail(h, e__, #call);      \
-  } while (0)
-
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-    else prev = -1;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
 
 void free_meter(ssb_analyzer* h) {
   cudaFree(h->st.filt); cudaFree(h->st.bucket); cudaFree(h->st.block_hist); cudaFree(h->st.st_hist);
@@ -173,6 +101,8 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
   return SSB_OK;
 }
 
+}  // namespace
+
 int32_t ensure_stage(ssb_analyzer* h, size_t floats) {
   if (floats <= h->stage_cap) return SSB_OK;
   CK(cudaStreamSynchronize(h->stream));
@@ -203,7 +133,7 @@ int32_t ensure_scratch(ssb_analyzer* h, size_t bytes) {
 }
 
 // enter every completed-but-ungated bucket into the histograms (separate launch)
-int32_t flush_gating(ssb_analyzer* h) {
+static int32_t flush_gating(ssb_analyzer* h) {
   const uint64_t done = h->total_frames / h->lp.s100;
   if (done > h->gated_upto) {
     CK(launch_gating(h->gp, h->st, h->gated_upto, done - 1, h->stream, &h->launches));
@@ -263,16 +193,31 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
   return SSB_OK;
 }
 
-int32_t refresh_results(ssb_analyzer* h) {
+int32_t launch_results_now(ssb_analyzer* h) {
+  const int aligned = (h->total_frames % h->lp.s100) == 0;
+  const uint64_t done = h->total_frames / h->lp.s100;
+  CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, h->d_results, h->stream, &h->launches,
+                    done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0));
+  if (done > h->gated_upto) h->gated_upto = done;
+  return SSB_OK;
+}
+
+const std::pair<std::vector<double>, std::vector<double>>& fft_axis_cached(ssb_analyzer* h, size_t n, uint32_t rate) {
+  auto key = std::make_pair(n, rate);
+  auto it = h->axes.find(key);
+  if (it == h->axes.end()) {
+    std::vector<double> x, t;
+    fft_axis(n, rate, x, t, nullptr);
+    it = h->axes.emplace(key, std::make_pair(std::move(x), std::move(t))).first;
+  }
+  return it->second;
+}
+
+static int32_t refresh_results(ssb_analyzer* h) {
   if (!h->meter_ok) return fail(h, SSB_ERR_NOMEM, "the loudness meter is not initialised (a previous create/reinit failed)");
   if (h->results_valid) return SSB_OK;
-  const int aligned = (h->total_frames % h->lp.s100) == 0;
-  {
-    const uint64_t done = h->total_frames / h->lp.s100;
-    CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, h->d_results, h->stream, &h->launches,
-                      done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0));
-    if (done > h->gated_upto) h->gated_upto = done;
-  }
+  const int32_t rrc = launch_results_now(h);
+  if (rrc) return rrc;
   const size_t stride = 4 + 2 * (size_t)h->channels;
   CK(cudaMemcpyAsync(h->h_results, h->d_results, h->n_streams * stride * sizeof(double), cudaMemcpyDeviceToHost,
                      h->stream));
@@ -338,7 +283,20 @@ int32_t fft_shape_check(size_t n, uint32_t rate) {
   return SSB_OK;
 }
 
-}  // namespace
+size_t waveform_window_columns(double waveform_window, size_t len, size_t* window_out) {
+  const double w = waveform_window * 1000.;
+  size_t window = 0;  // Rust `as usize` saturates; NaN -> 0
+  if (w > 0.0) window = w >= 18446744073709551615.0 ? SIZE_MAX : (size_t)w;
+  *window_out = window;
+  if (!window || !len) return 0;
+  const double spp = (double)len / (double)window;
+  // the loop breaks at the first column whose start is past the end (analyzer.rs:122-124); starts are monotone
+  size_t cols = window;
+  while (cols > 0 && (size_t)((double)(cols - 1) * spp) >= len) cols--;
+  return cols;
+}
+
+}  // namespace ssb
 
 extern "C" {
 
@@ -407,6 +365,7 @@ void ssb_analyzer_destroy(ssb_analyzer* h) {
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
   cudaFree(h->d_scratch);
+  cudaFree(h->d_pcm);
   if (h->h_scratch) cudaFreeHost(h->h_scratch);
   for (auto& ev : h->prof_events) {
     cudaEventDestroy(ev.first);
@@ -735,15 +694,9 @@ int32_t ssb_get_fft(ssb_analyzer* h, const float* samples, size_t n, double* xy_
   const float* db = static_cast<const float*>(h->h_scratch);
   const int32_t status = *reinterpret_cast<const int32_t*>(db + nb);
   if (status) return fail(h, status, "get_fft: window rejected (%d)", status);
-  auto key = std::make_pair(n, h->rate);
-  auto it = h->axes.find(key);
-  if (it == h->axes.end()) {
-    std::vector<double> x, t;
-    fft_axis(n, h->rate, x, t, nullptr);
-    it = h->axes.emplace(key, std::make_pair(std::move(x), std::move(t))).first;
-  }
-  const std::vector<double>& ax = it->second.first;
-  const std::vector<double>& tilt = it->second.second;
+  const auto& axes = fft_axis_cached(h, n, h->rate);
+  const std::vector<double>& ax = axes.first;
+  const std::vector<double>& tilt = axes.second;
   for (size_t i = 0; i < nb; i++) {
     xy_out[2 * i] = ax[i];
     xy_out[2 * i + 1] = (double)db[i] + tilt[i];  // analyzer.rs:82-84: val as f64 + compensation
@@ -791,10 +744,8 @@ int32_t ssb_process_tick(ssb_analyzer* h, const float* tail, size_t n_fft, size_
   const int aligned = (h->total_frames % h->lp.s100) == 0;
   if (!h->st.ring && !aligned) *lufs_status = *lufs_status ? *lufs_status : SSB_ERR_UNALIGNED_QUERY;
   {
-    const uint64_t done = h->total_frames / h->lp.s100;
-    CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, h->d_results, h->stream, &h->launches,
-                      done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0));
-    if (done > h->gated_upto) h->gated_upto = done;
+    const int32_t rrc = launch_results_now(h);
+    if (rrc) return rrc;
   }
   CK(cudaMemcpyAsync(h->h_results, h->d_results, stride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -805,15 +756,9 @@ int32_t ssb_process_tick(ssb_analyzer* h, const float* tail, size_t n_fft, size_
     const float* db = static_cast<const float*>(h->h_scratch);
     const int32_t* st = reinterpret_cast<const int32_t*>(db + 2 * nb);
     *fft_status = st[0] ? st[0] : st[1];
-    auto key = std::make_pair(n_fft, h->rate);
-    auto it = h->axes.find(key);
-    if (it == h->axes.end()) {
-      std::vector<double> x, t;
-      fft_axis(n_fft, h->rate, x, t, nullptr);
-      it = h->axes.emplace(key, std::make_pair(std::move(x), std::move(t))).first;
-    }
-    const std::vector<double>& ax = it->second.first;
-    const std::vector<double>& tilt = it->second.second;
+    const auto& axes = fft_axis_cached(h, n_fft, h->rate);
+    const std::vector<double>& ax = axes.first;
+    const std::vector<double>& tilt = axes.second;
     for (size_t i = 0; i < nb; i++) {
       xy_mid[2 * i] = ax[i];
       xy_mid[2 * i + 1] = (double)db[i] + tilt[i];
@@ -822,19 +767,6 @@ int32_t ssb_process_tick(ssb_analyzer* h, const float* tail, size_t n_fft, size_
     }
   }
   return SSB_OK;
-}
-
-static size_t waveform_window_columns(double waveform_window, size_t len, size_t* window_out) {
-  const double w = waveform_window * 1000.;
-  size_t window = 0;  // Rust `as usize` saturates; NaN -> 0
-  if (w > 0.0) window = w >= 18446744073709551615.0 ? SIZE_MAX : (size_t)w;
-  *window_out = window;
-  if (!window || !len) return 0;
-  const double spp = (double)len / (double)window;
-  // the loop breaks at the first column whose start is past the end (analyzer.rs:122-124); starts are monotone
-  size_t cols = window;
-  while (cols > 0 && (size_t)((double)(cols - 1) * spp) >= len) cols--;
-  return cols;
 }
 
 int32_t ssb_waveform_device(ssb_analyzer* h, const float* d_samples, size_t len, double waveform_window,

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(ssb):
 
 
 def test_abi_version(ssb):
-    assert ssb.lib().ssb_abi_version() == 1
+    assert ssb.lib().ssb_abi_version() == 2
 
 
 def test_no_cpu_fallback(ssb):

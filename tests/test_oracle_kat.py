@@ -296,3 +296,69 @@ def test_golden_regression(oracle):
         m.add_frames_f32(sw[off:off + 9600])
     got = [m.loudness_momentary(), m.loudness_shortterm(), m.loudness_global(), m.loudness_range(), m.true_peak(0), m.true_peak(1)]
     assert np.array_equal(got, g["sweep_scalars"])
+
+
+# ---- formats either side of the path: oracle/capture_ref.py -------------------------
+
+def test_pcm_rules_known_values(oracle):
+    """symphonia-core `FromSample<S> for f32`: full-scale and mid-scale values of every integer format."""
+    R = oracle.capture_ref
+    assert list(R.pcm_to_f32(bytes([0, 128, 255]), "u8")) == [-1.0, 0.0, 0.9921875]
+    assert list(R.pcm_to_f32(bytes([0x80, 0x00, 0x7f]), "s8")) == [-1.0, 0.0, 0.9921875]
+    assert list(R.pcm_to_f32(np.array([-32768, 0, 32767, 1], "<i2").tobytes(), "s16le")) == [-1.0, 0.0, 0.999969482421875, 2.0 ** -15]
+    assert list(R.pcm_to_f32(np.array([-32768, 32767], ">i2").tobytes(), "s16be")) == [-1.0, 0.999969482421875]
+    assert list(R.pcm_to_f32(bytes([0x00, 0x00, 0x80, 0xff, 0xff, 0x7f, 0x01, 0x00, 0x00]), "s24le")) == [-1.0, 1 - 2.0 ** -23, 2.0 ** -23]
+    assert list(R.pcm_to_f32(bytes([0x80, 0x00, 0x00, 0x7f, 0xff, 0xff]), "s24be")) == [-1.0, 1 - 2.0 ** -23]
+    # 2^31 - 1 is not representable in f32: the single rounding goes UP to 1.0; 2^31 - 129 is the tie that stays below
+    got = R.pcm_to_f32(np.array([-2 ** 31, 2 ** 31 - 1, 2 ** 31 - 128, 2 ** 31 - 129, 1], "<i4").tobytes(), "s32le")
+    assert list(got) == [-1.0, 1.0, 1.0 - 2.0 ** -24, 1.0 - 2.0 ** -24, 2.0 ** -31]
+    bits = np.array([0x7fc00001, 0xff800000, 0x00000001, 0x3f800000], "<u4")
+    assert np.array_equal(R.pcm_to_f32(bits.tobytes(), "f32le").view(np.uint32), bits)       # identity, NaN payload kept
+    assert np.array_equal(R.pcm_to_f32(bits.astype(">u4").tobytes(), "f32be").view(np.uint32), bits)
+    assert list(R.pcm_to_f32(np.array([0.1, 1e39, -1e-46], "<f8").tobytes(), "f64le")) == [np.float32(0.1), np.inf, -0.0]
+
+
+def test_pcm_rules_insensitive_to_spelling(oracle):
+    """The crate is un-vendored; both plausible spellings of each rule give the same bits (exhaustive for 8/16-bit)."""
+    R = oracle.capture_ref
+    rng = np.random.default_rng(0)
+    cases = {"u8": np.arange(256, dtype=np.uint8).tobytes(), "s16le": np.arange(-32768, 32768).astype("<i2").tobytes(),
+             "s16be": np.arange(-32768, 32768).astype(">i2").tobytes(),
+             "s24le": rng.integers(0, 256, 3 * 200000, dtype=np.uint8).tobytes(),
+             "s24be": rng.integers(0, 256, 3 * 200000, dtype=np.uint8).tobytes()}
+    for fmt, raw in cases.items():
+        assert np.array_equal(R.pcm_to_f32(raw, fmt).view(np.uint32), R.pcm_to_f32_alt(raw, fmt).view(np.uint32)), fmt
+    # s32: `(s as f64 / 2^31) as f32` vs `s as f32 / 2^31` — one rounding either way
+    raw = np.concatenate([rng.integers(-2 ** 31, 2 ** 31, 500000), [2 ** 31 - 1, -2 ** 31, 2 ** 24 + 1, 2 ** 25 + 3]]).astype("<i4").tobytes()
+    assert np.array_equal(R.pcm_to_f32(raw, "s32le").view(np.uint32), R.pcm_to_f32_alt(raw, "s32le").view(np.uint32))
+
+
+def test_capture_ring_mono_quirk(oracle):
+    """audio_capture.rs:43-48: `[x0, 0, x1, 0, x2]` — 2n-1 values per callback, so the L/R parity flips."""
+    r = oracle.capture_ref.RingRef(10)
+    r.callback([1, 2, 3], True)
+    assert list(r.to_vec()) == [0, 0, 0, 0, 0, 1, 0, 2, 0, 3]
+    r.callback([4, 5], True)
+    assert list(r.to_vec()) == [0, 0, 1, 0, 2, 0, 3, 4, 0, 5]      # 3 and 4 now share a stereo frame
+    r.callback(np.arange(10, 23), False)                             # oversize push: the last 10 survive
+    assert list(r.to_vec()) == list(range(13, 23))
+    r.callback([], True)
+    assert list(r.to_vec()) == list(range(13, 23))
+
+
+def test_mic_tick_oracle_composition(oracle):
+    """tui.rs:1427-1480 on the oracle: slices at 15*rate / 30*rate, waveform of mid over the whole ring."""
+    rate = 44100
+    ring = oracle.capture_ref.RingRef(30 * rate)
+    t = np.arange(15 * rate) / rate
+    x = np.empty(30 * rate, dtype=np.float32)
+    x[0::2] = 0.5 * np.sin(2 * np.pi * 1000 * t)
+    x[1::2] = 0.5 * np.sin(2 * np.pi * 1000 * t)
+    ring.callback(x, False)
+    a = oracle.Analyzer()
+    mid_fft, side_fft, wave, st, err = oracle.capture_ref.mic_tick(ring.to_vec(), a)
+    assert err is None and mid_fft.shape == (7423, 2) and wave.shape == (30000, 2)
+    assert side_fft[:, 1].max() == -150.0 + 10 * np.log10(20000.0 / 1000.0) or side_fft[:, 1].max() < -100    # L == R: silent side
+    assert abs(mid_fft[np.argmax(mid_fft[:, 1]), 1] - (20 * np.log10(0.5 * 4 / 2 / 2) + 0.0)) < 2.0   # Hann coherent gain 0.5
+    # 8192 frames of a -6 dBFS-peak stereo 1 kHz tone in a 3 s window: 10*log10(2 * 0.125 * 8192 / 132300) = -18.10
+    assert abs(st - (-18.10)) < 0.05
