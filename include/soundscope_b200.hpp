@@ -90,11 +90,86 @@ class Analyzer {
     return {std::move(mid), std::move(side)};
   }
 
+  // One player tick, tui.rs:1482-1552 (analyze_audio_file_samples): `tail` = the last n_fft stereo frames
+  struct Tick {
+    std::vector<std::pair<double, double>> mid_fft, side_fft;   // empty when get_fft would return Err
+    std::vector<std::pair<double, double>> waveform;            // microphone tick only
+    double shortterm_lufs = 0;
+    int32_t fft_status = 0, lufs_status = 0;
+  };
+  Tick process_tick(const std::vector<float>& tail, size_t lufs_samples = 16384) {
+    Tick t;
+    const size_t n_fft = tail.size() / 2, cap = n_fft / 2 + 1;
+    t.mid_fft.resize(cap);
+    t.side_fft.resize(cap);
+    size_t n = 0;
+    check(ssb_process_tick(h_, tail.data(), n_fft, lufs_samples, reinterpret_cast<double*>(t.mid_fft.data()),
+                           reinterpret_cast<double*>(t.side_fft.data()), cap, &n, &t.shortterm_lufs, &t.fft_status,
+                           &t.lufs_status));
+    t.mid_fft.resize(t.fft_status ? 0 : n);
+    t.side_fft.resize(t.fft_status ? 0 : n);
+    return t;
+  }
+
+  // One microphone tick, tui.rs:1427-1480 (analyze_microphone_input), on one snapshot of the capture ring
+  Tick analyze_microphone_input(ssb_capture_ring* ring, size_t n_fft = 16384, size_t lufs_samples = 16384,
+                                double waveform_window = 15.0) {
+    Tick t;
+    const size_t cap = n_fft / 2 + 1;
+    const double w = waveform_window * 1000.0;
+    const size_t wave_cap = 2 * (w > 0 ? (size_t)w : 0) + 2;
+    t.mid_fft.resize(cap);
+    t.side_fft.resize(cap);
+    t.waveform.resize(wave_cap);
+    size_t n = 0, nw = 0;
+    check(ssb_mic_tick(h_, ring, n_fft, lufs_samples, waveform_window, reinterpret_cast<double*>(t.mid_fft.data()),
+                       reinterpret_cast<double*>(t.side_fft.data()), cap, &n, reinterpret_cast<double*>(t.waveform.data()),
+                       wave_cap, &nw, &t.shortterm_lufs, &t.fft_status, &t.lufs_status));
+    t.mid_fft.resize(t.fft_status ? 0 : n);
+    t.side_fft.resize(t.fft_status ? 0 : n);
+    t.waveform.resize(nw);
+    return t;
+  }
+
+  // AudioFile::decode_file's sample conversion for WAV / AIFF PCM (audio_player.rs:248): raw interleaved PCM -> f32
+  std::vector<float> pcm_to_f32(const void* pcm, size_t n_samples, int32_t format) const {
+    std::vector<float> out(n_samples);
+    check(ssb_pcm_to_f32(h_, pcm, n_samples, format, out.data()));
+    return out;
+  }
+
   ssb_analyzer* handle() const { return h_; }
 
  private:
   void check(int32_t rc) const { if (rc) throw Error(rc, ssb_last_error(h_)); }
   ssb_analyzer* h_ = nullptr;
+};
+
+// `RBuffer` (tui.rs:37): AllocRingBuffer<f32>::new(capacity) + fill(0.0), written by the cpal callback
+// (audio_capture.rs:40-52).  push() is the callback body; the consumer is Analyzer::analyze_microphone_input.
+class CaptureRing {
+ public:
+  explicit CaptureRing(size_t capacity, int device = -1) {
+    const int32_t rc = ssb_capture_ring_create(&r_, capacity, device);
+    if (rc) throw Error(rc, "ssb_capture_ring_create");
+  }
+  ~CaptureRing() { ssb_capture_ring_destroy(r_); }
+  CaptureRing(const CaptureRing&) = delete;
+  CaptureRing& operator=(const CaptureRing&) = delete;
+  void push(const float* data, size_t n, bool is_mono) {
+    const int32_t rc = ssb_capture_ring_push(r_, data, n, is_mono ? 1 : 0);
+    if (rc) throw Error(rc, "ssb_capture_ring_push");
+  }
+  std::vector<float> to_vec() {
+    std::vector<float> out(ssb_capture_ring_capacity(r_));
+    const int32_t rc = ssb_capture_ring_to_vec(r_, out.data(), out.size());
+    if (rc) throw Error(rc, "ssb_capture_ring_to_vec");
+    return out;
+  }
+  ssb_capture_ring* handle() const { return r_; }
+
+ private:
+  ssb_capture_ring* r_ = nullptr;
 };
 
 }  // namespace soundscope

@@ -19,6 +19,14 @@ int main() {
     auto fft = a.get_fft(x);
     auto wf = a.get_waveform(x, 1.0);
     auto ms = a.get_mid_and_side_samples(x);
+    soundscope::CaptureRing ring(30 * 48000);
+    ring.push(x.data(), x.size(), false);
+    ring.push(x.data(), 100, true);
+    auto mic = a.analyze_microphone_input(ring.handle());
+    auto tick = a.process_tick(std::vector<float>(32768, 0.0f));
+    const short pcm[4] = {0, 16384, -32768, 32767};
+    auto f = a.pcm_to_f32(pcm, 4, SSB_PCM_S16LE);
+    if (f[1] != 0.5f || f[2] != -1.0f || mic.waveform.size() != 30000 || tick.mid_fft.size() != 6820) return 2;
     std::printf("%f %zu %zu %zu\n", a.get_integrated_lufs(), fft.size(), wf.size(), ms.first.size());
   } catch (const soundscope::Error& e) {
     std::printf("error %d %s\n", e.code, e.what());
@@ -27,6 +35,15 @@ int main() {
   return 0;
 }
 '''
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_runs_on_gpu(ssb, cuda):
+    """the same program on the GPU box: every mirror method returns reference-shaped results"""
+    test_cpp_mirror_compiles_links_and_fails_loudly_without_gpu(ssb)
 
 
 def test_cpp_mirror_compiles_links_and_fails_loudly_without_gpu(ssb):

@@ -232,3 +232,29 @@ def test_mic_tick_errors(ssb, oracle, cuda):
     a.create_loudness_meter(3, 22050)        # 16384 values are not a whole number of 3-channel frames -> NoMem
     got = a.analyze_microphone_input(small)
     assert got[5] == 1
+
+
+def test_golden_capture_vectors(ssb, cuda):
+    """the committed vectors (tests/golden/golden_capture_v1.npz): PCM bits, ring contents, one microphone tick"""
+    import os
+    from tests.golden import make_golden_capture as M
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_capture_v1.npz"))
+    a = ssb.Analyzer()
+    for fmt in M.FORMATS:
+        got = ssb.pcm_to_f32(a, g[f"pcm_{fmt}_raw"].tobytes(), fmt)
+        assert np.array_equal(_bits(got), g[f"pcm_{fmt}_f32bits"]), fmt
+    r = ssb.CaptureRing(M.RING_CAP)
+    for d, mono in M.ring_pushes():
+        r.push(d, bool(mono))
+    assert np.array_equal(_bits(r.to_vec()), _bits(g["ring_to_vec"]))
+    rate = 44100
+    ring = ssb.CaptureRing(30 * rate)
+    x = M.mic_signal(rate)
+    ring.push(x[: x.size // 2 + 1])
+    ring.push(x[x.size // 2 + 1:])
+    mid, side, wave, st, fs, ls = a.analyze_microphone_input(ring)     # default meter: 2 ch, 44100
+    assert fs == 0 and ls == 0
+    assert_db_close(mid[:, 1], g["mic_mid_db"])
+    assert_db_close(side[:, 1], g["mic_side_db"])
+    assert np.array_equal(wave[:, 1].astype(np.float32), g["mic_wave"])
+    assert abs(st - g["mic_shortterm"][0]) <= 1e-9

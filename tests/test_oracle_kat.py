@@ -362,3 +362,17 @@ def test_mic_tick_oracle_composition(oracle):
     assert abs(mid_fft[np.argmax(mid_fft[:, 1]), 1] - (20 * np.log10(0.5 * 4 / 2 / 2) + 0.0)) < 2.0   # Hann coherent gain 0.5
     # 8192 frames of a -6 dBFS-peak stereo 1 kHz tone in a 3 s window: 10*log10(2 * 0.125 * 8192 / 132300) = -18.10
     assert abs(st - (-18.10)) < 0.05
+
+
+def test_golden_capture_regression(oracle):
+    """oracle/capture_ref.py against the committed vectors (tests/golden/make_golden_capture.py)."""
+    from tests.golden import make_golden_capture as M
+    g = np.load(os.path.join(os.path.dirname(GOLD), "golden_capture_v1.npz"))
+    for fmt in M.FORMATS:
+        raw = M.pcm_raw(fmt)
+        assert np.array_equal(raw, g[f"pcm_{fmt}_raw"])
+        assert np.array_equal(oracle.capture_ref.pcm_to_f32(raw.tobytes(), fmt).view(np.uint32), g[f"pcm_{fmt}_f32bits"]), fmt
+    r = oracle.capture_ref.RingRef(M.RING_CAP)
+    for d, mono in M.ring_pushes():
+        r.callback(d, bool(mono))
+    assert np.array_equal(r.to_vec().view(np.uint32), g["ring_to_vec"].view(np.uint32))
