@@ -64,6 +64,16 @@ def make_input_device(torch, n_streams, frames, seed, device):
     return x.to(torch.float32).contiguous()
 
 
+def make_input_device_chunked(torch, n_streams, frames, seed, device, chunk=4096, channels=None):
+    """The same generator filled in slices of `chunk` streams, so its f64 temporaries stay small next to a large batch."""
+    ch = channels or CHANNELS
+    x = torch.empty((n_streams, frames, ch), dtype=torch.float32, device=device)
+    for s0 in range(0, n_streams, chunk):
+        n = min(chunk, n_streams - s0)
+        x[s0:s0 + n] = make_input_device(torch, n, frames, seed + s0, device)
+    return x
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -341,9 +351,7 @@ def run_ours(args):
             hbm = float(measured_peaks()[0].get("hbm_gbs", 6650.0))
             # BASELINE config 4's per-GPU shard: 125 000 stereo streams (10^6 over 8 GPUs), one 400 ms frame per step
             n5 = 125000
-            x5 = torch.empty((n5, FRAMES, CHANNELS), dtype=torch.float32, device=dev)
-            for s0 in range(0, n5, 5000):  # filled in slices: the generator's f64 temporaries stay small
-                x5[s0:s0 + 5000] = make_input_device(torch, min(5000, n5 - s0), FRAMES, 777 + s0, dev)
+            x5 = make_input_device_chunked(torch, n5, FRAMES, 777, dev, chunk=5000)
             an5 = S.BatchAnalyzer(n5, CHANNELS, RATE, S.MODE_LOUDNESS, device=local)
             res5 = torch.empty((n5, an5.stride), dtype=torch.float64, device=dev)
             for i in range(2):

@@ -489,11 +489,17 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 // recursion serially (10 DFMA + 1 F2F per sample: no zero-state pass, no hand-off), on the same TMA /
 // SWIZZLE_128B staging with [128 streams x 64 frames] tiles and a register-resident true-peak history.
 // ------------------------------------------------------------------------------------------------
+#ifndef SSB_SERIAL_F
+#define SSB_SERIAL_F 64
+#endif
+#ifndef SSB_SERIAL_MINB
+#define SSB_SERIAL_MINB 1
+#endif
 constexpr int kRowsSerial = 128;
-constexpr int kSerialF = 64;
+constexpr int kSerialF = SSB_SERIAL_F;
 
 template <int C, int TPF>
-__global__ void __launch_bounds__(kRowsSerial* C + 32, 1)
+__global__ void __launch_bounds__(kRowsSerial* C + 32, SSB_SERIAL_MINB)
 k_loudness_rows(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileArgs a) {
   constexpr int F = kSerialF;
   constexpr int RW = 32 / C;                       // rows per warp
@@ -644,10 +650,10 @@ constexpr int kAnyWarps = 8;
 
 template <int TPF>
 __global__ void __launch_bounds__(kAnyWarps * 32 + 32, 2)
-k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileArgs a, const int C) {
+k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileArgs a, const int C,
+                    const int ROWS) {   // ROWS: streams per TMA box (<= kAnyWarps * RW), the most any CTA owns
   constexpr int F = kAnyF;
   const int RW = 32 / C;                 // streams per warp
-  const int ROWS = kAnyWarps * RW;       // streams per CTA (multiple of 8)
   const unsigned STAGE_BYTES = (unsigned)C * ROWS * 128u;
 
   extern __shared__ unsigned char smem_raw[];
@@ -658,8 +664,10 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const unsigned row0 = blockIdx.x * (unsigned)ROWS;
-  const unsigned nrows = min((unsigned)ROWS, a.n_streams - row0);
+  // streams are split evenly over the grid (a multiple of the resident CTA slots): <= ROWS per CTA by construction
+  const unsigned row0 = (unsigned)(((unsigned long long)blockIdx.x * a.n_streams) / gridDim.x);
+  const unsigned row1 = (unsigned)(((unsigned long long)(blockIdx.x + 1) * a.n_streams) / gridDim.x);
+  const unsigned nrows = row1 - row0;
   const unsigned live_warps = (nrows + RW - 1) / RW;
 
   if (tid == 0) {
@@ -713,39 +721,47 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
     mbar_wait_warp(&full[s], (tile / kStages) & 1);
     const unsigned char* row_base = stages + (size_t)s * 32768 + (size_t)(lane_ok ? r : 0) * 128;
     const unsigned to_boundary = a.s100 - pos;
+    // one sample of this lane's channel: peaks, K-weighting step, y^2 into the bucket in progress
+#define SSB_ANY_SAMPLE(f)                                                                                   \
+    {                                                                                                       \
+      const int fi = (f) * C + (lane_ok ? c : 0);                                                           \
+      const float xf = *reinterpret_cast<const float*>(row_base + (size_t)(fi >> 5) * ROWS * 128 +          \
+                                                        ((((fi >> 2) & 7) ^ key) << 4) + ((fi & 3) << 2));  \
+      sp = fmaxf(sp, fabsf(xf));                                                                            \
+      if (TPF == 4) {                                                                                       \
+        _Pragma("unroll") for (int ph = 0; ph < 3; ph++) {                                                  \
+          float accf = xf * a.tp4[ph][0];                                                                   \
+          _Pragma("unroll") for (int t = 1; t < 12; t++) accf = fmaf(w[t - 1], a.tp4[ph][t], accf);         \
+          tp = fmaxf(tp, fabsf(accf));                                                                      \
+        }                                                                                                   \
+      } else if (TPF == 2) {                                                                                \
+        float accf = xf * a.tp2[0];                                                                         \
+        _Pragma("unroll") for (int t = 1; t < 24; t++) accf = fmaf(w[t - 1], a.tp2[t], accf);               \
+        tp = fmaxf(tp, fabsf(accf));                                                                        \
+      }                                                                                                     \
+      if (TPF != 0) {                                                                                       \
+        _Pragma("unroll") for (int t = TPW - 1; t > 0; t--) w[t] = w[t - 1];                                \
+        w[0] = xf;                                                                                          \
+      }                                                                                                     \
+      SSB_FILTER_STEP(SSB_CVT(xf))                                                                          \
+      acc = fma(y_, y_, acc);                                                                               \
+    }
+    if (to_boundary > (unsigned)F) {
+      // the usual tile (299 of 300 at 96 kHz): no bucket ends inside it, the loop carries no boundary test
 #pragma unroll 4
-    for (int f = 0; f < F; f++) {
-      const int fi = f * C + (lane_ok ? c : 0);
-      const float xf = *reinterpret_cast<const float*>(row_base + (size_t)(fi >> 5) * ROWS * 128 +
-                                                        ((((fi >> 2) & 7) ^ key) << 4) + ((fi & 3) << 2));
-      sp = fmaxf(sp, fabsf(xf));
-      if (TPF == 4) {
-#pragma unroll
-        for (int ph = 0; ph < 3; ph++) {
-          float accf = xf * a.tp4[ph][0];
-#pragma unroll
-          for (int t = 1; t < 12; t++) accf = fmaf(w[t - 1], a.tp4[ph][t], accf);
-          tp = fmaxf(tp, fabsf(accf));
+      for (int f = 0; f < F; f++) SSB_ANY_SAMPLE(f)
+    } else {
+#pragma unroll 1
+      for (int f = 0; f < F; f++) {
+        SSB_ANY_SAMPLE(f)
+        if (f + 1 == (int)to_boundary) {   // the bucket in progress is complete
+          if (live) a.bucket[gidx * kNB + slot] = acc;
+          acc = 0.0;
+          slot = (slot + 1) % kNB;
         }
-      } else if (TPF == 2) {
-        float accf = xf * a.tp2[0];
-#pragma unroll
-        for (int t = 1; t < 24; t++) accf = fmaf(w[t - 1], a.tp2[t], accf);
-        tp = fmaxf(tp, fabsf(accf));
-      }
-      if (TPF != 0) {
-#pragma unroll
-        for (int t = TPW - 1; t > 0; t--) w[t] = w[t - 1];
-        w[0] = xf;
-      }
-      SSB_FILTER_STEP(SSB_CVT(xf))
-      acc = fma(y_, y_, acc);
-      if (f + 1 == (int)to_boundary) {
-        if (live) a.bucket[gidx * kNB + slot] = acc;
-        acc = 0.0;
-        slot = (slot + 1) % kNB;
       }
     }
+#undef SSB_ANY_SAMPLE
     pos = to_boundary > (unsigned)F ? pos + F : (unsigned)F - to_boundary;
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
@@ -896,7 +912,8 @@ cudaError_t launch_rows_c(const CUtensorMap& tmap, const TileArgs& args, unsigne
 
 
 template <int TPF>
-cudaError_t launch_any_cfg(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, int C, cudaStream_t s) {
+cudaError_t launch_any_cfg(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, int C, int box_rows,
+                           cudaStream_t s) {
   auto kern = k_loudness_rows_any<TPF>;
   const size_t smem = (size_t)kStages * 32768 + 2 * kStages * sizeof(uint64_t) + 1024;
   static bool configured_dev[64] = {false};
@@ -908,7 +925,7 @@ cudaError_t launch_any_cfg(const CUtensorMap& tmap, const TileArgs& args, unsign
     if (e) return e;
     configured = true;
   }
-  kern<<<n_ctas, kAnyWarps * 32 + 32, smem, s>>>(tmap, args, C);
+  kern<<<n_ctas, kAnyWarps * 32 + 32, smem, s>>>(tmap, args, C, box_rows);
   return cudaGetLastError();
 }
 
@@ -954,7 +971,25 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   const bool any_c = C > 2;
   const bool serial = any_c || force_kernel == 2 || (force_kernel != 3 && st.n_streams >= serial_min_streams());
   const int tile_f = any_c ? kAnyF : (serial ? kSerialF : kTileFMax);
-  const int box_rows = any_c ? kAnyWarps * (32 / C) : (serial ? kRowsSerial : kRows);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  int box_rows = any_c ? kAnyWarps * (32 / C) : (serial ? kRowsSerial : kRows);
+  size_t any_ctas = 0;
+  if (any_c) {
+    // two CTAs fit an SM: the grid is the smallest multiple of 2 * SMs that keeps <= box_rows streams per CTA, so every
+    // SM carries the same number of streams (few streams: one CTA per box), and the TMA box shrinks to what a CTA owns
+    any_ctas = (st.n_streams + box_rows - 1) / box_rows;
+    if (st.n_streams >= (size_t)(2 * sms)) {
+      const size_t slots = 2 * (size_t)sms;
+      any_ctas = (any_ctas + slots - 1) / slots * slots;
+    }
+    box_rows = (int)((st.n_streams + any_ctas - 1) / any_ctas);
+  }
   const size_t n_tiles = frames / tile_f;
   if (!n_tiles) return cudaSuccess;
   const size_t row_floats = in_stride_frames * C;
@@ -992,19 +1027,13 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   a.slot0 = (unsigned)(bucket0 % kNB);
   a.do_sample_peak = p.do_sample_peak;
 
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
   const int tpf = p.do_true_peak ? p.tp_factor : 0;
   cudaError_t e;
   if (any_c) {
-    const size_t n_ctas = (st.n_streams + box_rows - 1) / box_rows;
-    e = tpf == 4 ? launch_any_cfg<4>(tmap, a, (unsigned)n_ctas, C, s)
-                 : (tpf == 2 ? launch_any_cfg<2>(tmap, a, (unsigned)n_ctas, C, s) : launch_any_cfg<0>(tmap, a, (unsigned)n_ctas, C, s));
+    const size_t n_ctas = any_ctas;
+    e = tpf == 4 ? launch_any_cfg<4>(tmap, a, (unsigned)n_ctas, C, box_rows, s)
+                 : (tpf == 2 ? launch_any_cfg<2>(tmap, a, (unsigned)n_ctas, C, box_rows, s)
+                             : launch_any_cfg<0>(tmap, a, (unsigned)n_ctas, C, box_rows, s));
   } else if (serial) {
     const size_t n_ctas = (st.n_streams + kRowsSerial - 1) / kRowsSerial;
     e = C == 1 ? launch_rows_c<1>(tmap, a, (unsigned)n_ctas, tpf, s) : launch_rows_c<2>(tmap, a, (unsigned)n_ctas, tpf, s);

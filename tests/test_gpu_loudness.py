@@ -360,3 +360,23 @@ def test_scan_kernel_few_streams(ssb, oracle, cuda, n, channels, rate, flags_nam
     for s in range(n):
         assert np.array_equal(scan.histograms(s)[0], ob._per_stream_hist(s)[0])
         assert np.array_equal(scan.histograms(s)[1], ob._per_stream_hist(s)[1])
+
+
+@pytest.mark.parametrize("n,channels,rate", [(2000, 6, 96000), (700, 3, 48000), (5000, 8, 48000), (296, 5, 44100)])
+def test_rows_any_even_split_matches_generic(ssb, cuda, n, channels, rate):
+    """k_loudness_rows_any spreads the streams evenly over a multiple of 2 x SMs CTAs (ragged 3..17 streams per CTA
+    here): same operation sequence as the thread-per-channel kernel -> identical result rows and histograms."""
+    torch = cuda
+    frames = (rate // 10) * 2 + 32 * 7 + 5      # two bucket boundaries, a ragged tail for the generic kernel
+    mode = ssb.MODE_ALL
+    x = torch.from_numpy(stream_batch(n, frames * 2, channels, seed=n, rate=rate)).cuda()
+    fast, slow = ssb.BatchAnalyzer(n, channels, rate, mode), ssb.BatchAnalyzer(n, channels, rate, mode)
+    slow.force_generic(True)
+    for k in range(2):
+        sl = x[:, k * frames:(k + 1) * frames, :].contiguous()
+        fast.add_frames_device(sl)
+        slow.add_frames_device(sl)
+    a, b = fast.results_device().cpu().numpy(), slow.results_device().cpu().numpy()
+    assert np.array_equal(a, b, equal_nan=True)
+    for s in (0, n // 2, n - 1):
+        assert np.array_equal(fast.histograms(s)[0], slow.histograms(s)[0])
