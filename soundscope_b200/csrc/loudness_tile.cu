@@ -648,10 +648,12 @@ k_loudness_rows(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 constexpr int kAnyF = 32;
 constexpr int kAnyWarps = 8;
 
-template <int TPF>
-__global__ void __launch_bounds__(kAnyWarps * 32 + 32, 2)
+// NS TMA stages of 32 KB, MINB CTAs per SM: without the true-peak FIR the kernel is latency-bound (one dependent
+// recursion per lane), so it trades a stage for a third resident CTA (24 compute warps per SM)
+template <int TPF, int NS, int MINB>
+__global__ void __launch_bounds__(kAnyWarps * 32 + 32, MINB)
 k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileArgs a, const int C,
-                    const int ROWS) {   // ROWS: streams per TMA box (<= kAnyWarps * RW), the most any CTA owns
+                    const int ROWS) {   // ROWS: streams per TMA box (multiple of 8, <= kAnyWarps * RW), >= what a CTA owns
   constexpr int F = kAnyF;
   const int RW = 32 / C;                 // streams per warp
   const unsigned STAGE_BYTES = (unsigned)C * ROWS * 128u;
@@ -659,8 +661,8 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stages = smem;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * 32768);  // stage <= 32 KB for every C
-  uint64_t* empty = full + kStages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * 32768);  // stage <= 32 KB for every C
+  uint64_t* empty = full + NS;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -671,7 +673,7 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
   const unsigned live_warps = (nrows + RW - 1) / RW;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; s++) {
+    for (int s = 0; s < NS; s++) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], live_warps);
     }
@@ -683,8 +685,8 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
   if (warp == kAnyWarps) {
     if (lane == 0 && live_warps > 0) {
       for (unsigned tile = 0; tile < a.n_tiles; tile++) {
-        const unsigned s = tile % kStages;
-        if (tile >= (unsigned)kStages) mbar_wait(&empty[s], ((tile / kStages) - 1) & 1);
+        const unsigned s = tile % NS;
+        if (tile >= (unsigned)NS) mbar_wait(&empty[s], ((tile / NS) - 1) & 1);
         mbar_expect_tx(&full[s], STAGE_BYTES);
         tma_load_3d(stages + (size_t)s * 32768, &tmap, &full[s], 0, (int)row0, (int)(tile * C));
       }
@@ -717,8 +719,8 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
   unsigned pos = a.pos0;
 
   for (unsigned tile = 0; tile < a.n_tiles; tile++) {
-    const unsigned s = tile % kStages;
-    mbar_wait_warp(&full[s], (tile / kStages) & 1);
+    const unsigned s = tile % NS;
+    mbar_wait_warp(&full[s], (tile / NS) & 1);
     const unsigned char* row_base = stages + (size_t)s * 32768 + (size_t)(lane_ok ? r : 0) * 128;
     const unsigned to_boundary = a.s100 - pos;
     // one sample of this lane's channel: peaks, K-weighting step, y^2 into the bucket in progress
@@ -911,11 +913,11 @@ cudaError_t launch_rows_c(const CUtensorMap& tmap, const TileArgs& args, unsigne
 }
 
 
-template <int TPF>
+template <int TPF, int NS, int MINB>
 cudaError_t launch_any_cfg(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, int C, int box_rows,
                            cudaStream_t s) {
-  auto kern = k_loudness_rows_any<TPF>;
-  const size_t smem = (size_t)kStages * 32768 + 2 * kStages * sizeof(uint64_t) + 1024;
+  auto kern = k_loudness_rows_any<TPF, NS, MINB>;
+  const size_t smem = (size_t)NS * 32768 + 2 * NS * sizeof(uint64_t) + 1024;
   static bool configured_dev[64] = {false};
   int dev_ = 0;
   cudaGetDevice(&dev_);
@@ -981,14 +983,17 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   int box_rows = any_c ? kAnyWarps * (32 / C) : (serial ? kRowsSerial : kRows);
   size_t any_ctas = 0;
   if (any_c) {
-    // two CTAs fit an SM: the grid is the smallest multiple of 2 * SMs that keeps <= box_rows streams per CTA, so every
-    // SM carries the same number of streams (few streams: one CTA per box), and the TMA box shrinks to what a CTA owns
+    // three (two with the true-peak FIR) CTAs fit an SM: the grid is the smallest multiple of the resident slots that
+    // keeps <= box_rows streams per CTA, so every SM carries the same number of streams (few streams: one CTA per
+    // box), and the TMA box shrinks to what a CTA owns
     any_ctas = (st.n_streams + box_rows - 1) / box_rows;
-    if (st.n_streams >= (size_t)(2 * sms)) {
-      const size_t slots = 2 * (size_t)sms;
+    const size_t slots = (size_t)((p.do_true_peak && p.tp_factor) ? 2 : 3) * (size_t)sms;
+    if (st.n_streams >= slots) {
       any_ctas = (any_ctas + slots - 1) / slots * slots;
     }
-    box_rows = (int)((st.n_streams + any_ctas - 1) / any_ctas);
+    // SWIZZLE_128B keys on shared-memory address bits 7..9 = (line * box_rows + row) & 7: a box of a multiple of 8 rows
+    // keeps that equal to row & 7 for every line
+    box_rows = (int)(((st.n_streams + any_ctas - 1) / any_ctas + 7) / 8 * 8);
   }
   const size_t n_tiles = frames / tile_f;
   if (!n_tiles) return cudaSuccess;
@@ -1031,9 +1036,9 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   cudaError_t e;
   if (any_c) {
     const size_t n_ctas = any_ctas;
-    e = tpf == 4 ? launch_any_cfg<4>(tmap, a, (unsigned)n_ctas, C, box_rows, s)
-                 : (tpf == 2 ? launch_any_cfg<2>(tmap, a, (unsigned)n_ctas, C, box_rows, s)
-                             : launch_any_cfg<0>(tmap, a, (unsigned)n_ctas, C, box_rows, s));
+    e = tpf == 4 ? launch_any_cfg<4, 3, 2>(tmap, a, (unsigned)n_ctas, C, box_rows, s)
+                 : (tpf == 2 ? launch_any_cfg<2, 3, 2>(tmap, a, (unsigned)n_ctas, C, box_rows, s)
+                             : launch_any_cfg<0, 2, 3>(tmap, a, (unsigned)n_ctas, C, box_rows, s));
   } else if (serial) {
     const size_t n_ctas = (st.n_streams + kRowsSerial - 1) / kRowsSerial;
     e = C == 1 ? launch_rows_c<1>(tmap, a, (unsigned)n_ctas, tpf, s) : launch_rows_c<2>(tmap, a, (unsigned)n_ctas, tpf, s);
