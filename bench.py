@@ -371,9 +371,9 @@ def run_ours(args):
                                                    "realtime_streams_equiv": n5 * FRAMES / RATE / (t5 * 1e-3),
                                                    "note": "filter + gating/results query per step, 19.2 GB resident input"}
             del an5, x5, res5
-            # BASELINE config 5 shape: 5.1 (6-channel) 96 kHz streams, Mode::all() = K-weighting + gating + sample peak + true peak
-            # (ebur128's rate rule picks the 2x interpolator at 96 kHz); 4096 streams x 400 ms
-            n6, f6 = 4096, 38400
+            # BASELINE config 5 shape: 16384 5.1 (6-channel) 96 kHz streams per GPU, 200 ms per step; Mode::all() = K-weighting +
+            # gating + sample peak + true peak (ebur128's rate rule picks the 2x interpolator at 96 kHz)
+            n6, f6 = 16384, 19200
             x6 = (torch.rand((n6, f6, 6), generator=g, device=dev) - 0.5).contiguous()
             for mode_name, md in (("loudness", S.MODE_LOUDNESS), ("all", S.MODE_ALL)):
                 an6 = S.BatchAnalyzer(n6, 6, 96000, md, device=local)

@@ -253,7 +253,13 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   }
   __syncthreads();
 
-  if (warp == NW) {
+#ifndef SSB_PRODUCER_IDLE_WARP
+#define SSB_PRODUCER_IDLE_WARP 0
+#endif
+  // The producer is the first warp without streams: with 27-28 streams per CTA (cfg2) that is warp 7, which shares its
+  // SM sub-partition with one compute warp only; the extra warp 8 would sit on sub-partition 0 beside two of them.
+  const int producer_warp = (SSB_PRODUCER_IDLE_WARP && live_warps < (unsigned)NW) ? (int)live_warps : NW;
+  if (warp == producer_warp) {
     // ---------------- producer warp: one elected lane drives TMA ----------------
     if (lane == 0 && live_warps > 0) {
       for (unsigned tile = 0; tile < a.n_tiles; tile++) {

@@ -10,7 +10,7 @@ torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev)
 g.manual_seed(1)
-n6, f6 = 4096, 38400
+n6, f6 = 16384, 9600
 x6 = (torch.rand((n6, f6, 6), generator=g, device=dev) - 0.5).contiguous()
 for md in (S.MODE_LOUDNESS, S.MODE_ALL):
     an = S.BatchAnalyzer(n6, 6, 96000, md, device=0)
