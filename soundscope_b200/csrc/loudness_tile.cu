@@ -254,7 +254,7 @@ k_loudness_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   __syncthreads();
 
 #ifndef SSB_PRODUCER_IDLE_WARP
-#define SSB_PRODUCER_IDLE_WARP 0
+#define SSB_PRODUCER_IDLE_WARP 1
 #endif
   // The producer is the first warp without streams: with 27-28 streams per CTA (cfg2) that is warp 7, which shares its
   // SM sub-partition with one compute warp only; the extra warp 8 would sit on sub-partition 0 beside two of them.

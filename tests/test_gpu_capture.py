@@ -258,3 +258,38 @@ def test_golden_capture_vectors(ssb, cuda):
     assert_db_close(side[:, 1], g["mic_side_db"])
     assert np.array_equal(wave[:, 1].astype(np.float32), g["mic_wave"])
     assert abs(st - g["mic_shortterm"][0]) <= 1e-9
+
+
+def test_capture_ring_concurrent_producer_snapshots_are_consistent(ssb, cuda):
+    """single producer (the capture callback's thread) pushing while the consumer snapshots: every snapshot is a
+    contiguous window of the pushed sequence (ctypes releases the GIL, so the two really overlap)"""
+    import threading
+    cap = 1 << 14
+    r = ssb.CaptureRing(cap)
+    stop = threading.Event()
+
+    def producer():
+        k = 1
+        while not stop.is_set() and k < (1 << 24) - 200:
+            n = 1 + (k % 97)
+            r.push(np.arange(k, k + n, dtype=np.float32))    # consecutive integers, exact in f32
+            k += n
+
+    t = threading.Thread(target=producer)
+    t.start()
+    good = 0
+    try:
+        for _ in range(400):
+            try:
+                v = r.to_vec()
+            except ssb.SsbError:
+                continue          # lapped four times in a row: refused, never a wrong answer
+            nz = np.flatnonzero(v)
+            if nz.size:
+                assert nz[-1] == cap - 1 and np.all(np.diff(nz) == 1)          # zeros (initial fill) come first
+                assert np.all(np.diff(v[nz[0]:]) == 1.0), "torn snapshot"
+            good += 1
+    finally:
+        stop.set()
+        t.join()
+    assert good > 0
