@@ -724,17 +724,42 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
   for (int t = 0; t < TPW; t++) w[t] = (TPF != 0 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
   unsigned pos = a.pos0;
 
+  // Where this lane's 32 samples of a tile sit inside a stage (swizzled): it depends on (row, channel) only, so the
+  // loudness-only variant keeps the byte offsets in registers, two 16-bit offsets per register (a stage is <= 32 KB),
+  // and the recursion loop spends one extract instead of ~8 address instructions per sample.  The true-peak
+  // variants have no registers to spare (3 CTAs x 288 threads leave 72 per thread) and compute the address.
+  constexpr bool kPackedOffsets = TPF == 0;
+  unsigned offp[kPackedOffsets ? F / 2 : 1];
+  if (kPackedOffsets) {
+#pragma unroll
+    for (int j = 0; j < F / 2; j++) {
+      unsigned o2[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int fi = (2 * j + h) * C + (lane_ok ? c : 0);
+        o2[h] = (unsigned)(lane_ok ? r : 0) * 128u + (unsigned)(fi >> 5) * (unsigned)ROWS * 128u +
+                (unsigned)((((fi >> 2) & 7) ^ key) << 4) + (unsigned)((fi & 3) << 2);
+      }
+      offp[j] = o2[0] | (o2[1] << 16);
+    }
+  }
+
   for (unsigned tile = 0; tile < a.n_tiles; tile++) {
     const unsigned s = tile % NS;
     mbar_wait_warp(&full[s], (tile / NS) & 1);
-    const unsigned char* row_base = stages + (size_t)s * 32768 + (size_t)(lane_ok ? r : 0) * 128;
+    const unsigned char* stage_base = stages + (size_t)s * 32768;
+    const unsigned char* row_base = stage_base + (size_t)(lane_ok ? r : 0) * 128;
     const unsigned to_boundary = a.s100 - pos;
     // one sample of this lane's channel: peaks, K-weighting step, y^2 into the bucket in progress
-#define SSB_ANY_SAMPLE(f)                                                                                   \
+#define SSB_ANY_LOAD_CALC(f)                                                                                 \
+    *reinterpret_cast<const float*>(row_base + (size_t)(((f) * C + (lane_ok ? c : 0)) >> 5) * ROWS * 128 +    \
+                                    ((((((f) * C + (lane_ok ? c : 0)) >> 2) & 7) ^ key) << 4) +               \
+                                    ((((f) * C + (lane_ok ? c : 0)) & 3) << 2))
+#define SSB_ANY_LOAD_PACKED(f) \
+    *reinterpret_cast<const float*>(stage_base + (((f) & 1) ? (offp[(f) >> 1] >> 16) : (offp[(f) >> 1] & 0xffffu)))
+#define SSB_ANY_SAMPLE(f, LOAD)                                                                             \
     {                                                                                                       \
-      const int fi = (f) * C + (lane_ok ? c : 0);                                                           \
-      const float xf = *reinterpret_cast<const float*>(row_base + (size_t)(fi >> 5) * ROWS * 128 +          \
-                                                        ((((fi >> 2) & 7) ^ key) << 4) + ((fi & 3) << 2));  \
+      const float xf = LOAD(f);                                                                             \
       sp = fmaxf(sp, fabsf(xf));                                                                            \
       if (TPF == 4) {                                                                                       \
         _Pragma("unroll") for (int ph = 0; ph < 3; ph++) {                                                  \
@@ -756,12 +781,17 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
     }
     if (to_boundary > (unsigned)F) {
       // the usual tile (299 of 300 at 96 kHz): no bucket ends inside it, the loop carries no boundary test
+      if (kPackedOffsets) {
+#pragma unroll
+        for (int f = 0; f < F; f++) SSB_ANY_SAMPLE(f, SSB_ANY_LOAD_PACKED)
+      } else {
 #pragma unroll 4
-      for (int f = 0; f < F; f++) SSB_ANY_SAMPLE(f)
+        for (int f = 0; f < F; f++) SSB_ANY_SAMPLE(f, SSB_ANY_LOAD_CALC)
+      }
     } else {
 #pragma unroll 1
       for (int f = 0; f < F; f++) {
-        SSB_ANY_SAMPLE(f)
+        SSB_ANY_SAMPLE(f, SSB_ANY_LOAD_CALC)
         if (f + 1 == (int)to_boundary) {   // the bucket in progress is complete
           if (live) a.bucket[gidx * kNB + slot] = acc;
           acc = 0.0;
@@ -770,6 +800,8 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
       }
     }
 #undef SSB_ANY_SAMPLE
+#undef SSB_ANY_LOAD_CALC
+#undef SSB_ANY_LOAD_PACKED
     pos = to_boundary > (unsigned)F ? pos + F : (unsigned)F - to_boundary;
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
