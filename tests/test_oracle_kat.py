@@ -376,3 +376,60 @@ def test_golden_capture_regression(oracle):
     for d, mono in M.ring_pushes():
         r.callback(d, bool(mono))
     assert np.array_equal(r.to_vec().view(np.uint32), g["ring_to_vec"].view(np.uint32))
+
+
+# ---- independent implementations (SURVEY §8(c) "secondary cross-checks") -----------------------------------
+def _program_like(rate, seconds, seed):
+    rng = np.random.default_rng(seed)
+    n = int(rate * seconds)
+    t = np.arange(n) / rate
+    left = 0.3 * np.sin(2 * np.pi * 440 * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 0.2 * t)) + 0.02 * rng.standard_normal(n)
+    right = 0.2 * np.sin(2 * np.pi * 660 * t) + 0.02 * rng.standard_normal(n)
+    return np.stack([left, right], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("rate", [44100, 48000, 96000])
+def test_oracle_against_scipy_lfilter(oracle, rate):
+    """The oracle's DF-II recursion + ring sums against scipy.signal.lfilter (an independent transposed-DF-II in f64)
+    and plain mean squares: momentary and short-term loudness agree to 1e-9 LU."""
+    from scipy import signal
+    x = _program_like(rate, 5.0, rate)
+    m = oracle.EbuR128(2, rate)
+    m.add_frames_f32(x.ravel())
+    b, a = m.coeffs()
+    y = signal.lfilter(b, a, x.astype(np.float64), axis=0)
+    s100 = (rate + 5) // 10
+    for frames, got in ((4 * s100, m.loudness_momentary()), (30 * s100, m.loudness_shortterm())):
+        want = -0.691 + 10 * np.log10(np.mean(y[-frames:] ** 2, axis=0).sum())
+        assert abs(got - want) < 1e-9
+
+
+def test_oracle_against_torchaudio_loudness(oracle):
+    """torchaudio.functional.loudness is an independent BS.1770 integrated-loudness implementation (exact block list
+    instead of ebur128's 0.1 LU histogram, its own K-weighting design): agreement within the histogram's quantisation."""
+    import torch
+    import torchaudio
+    for seed, rate in ((1, 48000), (2, 44100)):
+        x = _program_like(rate, 10.0, seed)
+        m = oracle.EbuR128(2, rate)
+        m.add_frames_f32(x.ravel())
+        ta = torchaudio.functional.loudness(torch.from_numpy(np.ascontiguousarray(x.T)), rate).item()
+        assert abs(m.loudness_global() - ta) < 0.1, (m.loudness_global(), ta)
+
+
+def test_oracle_true_peak_against_polyphase_resampler(oracle):
+    """ebur128's 49-tap interpolator against scipy's (longer) polyphase resampler: inter-sample peaks within 2 %, and a
+    fs/4 tone sampled 45 degrees off its crests reads +3 dB over the sample peak (the EBU 3341 true-peak construction)."""
+    from scipy import signal
+    x = _program_like(48000, 4.0, 3)
+    m = oracle.EbuR128(2, 48000)
+    m.add_frames_f32(x.ravel())
+    up = np.abs(signal.resample_poly(x.astype(np.float64), 4, 1, axis=0)).max(axis=0)
+    for c in range(2):
+        assert abs(m.true_peak(c) / up[c] - 1.0) < 0.02
+    n = np.arange(48000)
+    tone = (0.5 * np.sin(2 * np.pi * 0.25 * n + np.pi / 4)).astype(np.float32)       # samples at +-0.3536, crests at 0.5
+    m = oracle.EbuR128(1, 48000)
+    m.add_frames_f32(tone)
+    assert abs(m.sample_peak(0) - 0.5 / np.sqrt(2)) < 1e-6
+    assert -0.4 <= 20 * np.log10(m.true_peak(0) / 0.5) <= 0.2          # EBU Tech 3341's true-peak tolerance
