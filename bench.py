@@ -332,6 +332,14 @@ def run_ours(args):
             for i in range(10):
                 single.calculate_integrated_lufs(2, whole)
             extras["integrated_lufs_10s_file_ms"] = (time.perf_counter() - t0) / 10 * 1e3
+            whole5 = np.tile(whole, 30)            # a 5-minute 48 kHz stereo file (115 MB)
+            for i in range(2):
+                single.calculate_integrated_lufs(2, whole5)
+            t0 = time.perf_counter()
+            for i in range(3):
+                single.calculate_integrated_lufs(2, whole5)
+            extras["integrated_lufs_5min_file_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+            del whole5
             # many-streams regime (BASELINE config 4 per-GPU shape, scaled to 32768 streams x 400 ms): serial kernel
             an4 = S.BatchAnalyzer(32768, CHANNELS, RATE, S.MODE_LOUDNESS, device=local)
             x4 = make_input_device(torch, 32768, FRAMES, 4321, dev)

@@ -115,14 +115,21 @@ int32_t ensure_stage(ssb_analyzer* h, size_t floats) {
   return SSB_OK;
 }
 
-int32_t ensure_scratch(ssb_analyzer* h, size_t bytes) {
+int32_t ensure_scratch_device(ssb_analyzer* h, size_t bytes) {
   if (bytes > h->scratch_cap) {
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(h->d_scratch);
     h->d_scratch = nullptr;
+    h->scratch_cap = 0;
     CK(cudaMalloc(&h->d_scratch, bytes));
     h->scratch_cap = bytes;
   }
+  return SSB_OK;
+}
+
+int32_t ensure_scratch(ssb_analyzer* h, size_t bytes) {
+  const int32_t drc = ensure_scratch_device(h, bytes);
+  if (drc) return drc;
   if (bytes > h->h_scratch_cap) {
     if (h->h_scratch) cudaFreeHost(h->h_scratch);
     h->h_scratch = nullptr;
@@ -582,7 +589,9 @@ int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const 
     tmp = h->oneshot = nullptr;
   }
   if (!tmp) {
-    rc = ssb_analyzer_create(&tmp, channels, h->rate, SSB_MODE_ALL, 1, h->device, 0);
+    // the reference builds the meter with Mode::all() (analyzer.rs:171) but reads only loudness_global(): the peak
+    // detectors' output is dropped with the meter, so this one computes K-weighting + gating only — same value
+    rc = ssb_analyzer_create(&tmp, channels, h->rate, SSB_MODE_I | SSB_MODE_HISTOGRAM, 1, h->device, 0);
     if (rc == SSB_ERR_NOMEM) return SSB_OK;  // EbuR128::new failed -> None
     if (rc) return fail(h, rc, "calculate_integrated_lufs: cannot create meter");
     h->oneshot = tmp;
@@ -599,15 +608,36 @@ int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const 
     if (n % channels != 0) ok = false;
   }
   if (ok && len) {
-    rc = ensure_scratch(tmp, len * sizeof(float));
+    const size_t frames = len / channels;
+    const uint32_t s100 = tmp->lp.s100;
+    const uint64_t n_buckets = frames / s100;             // complete 100 ms buckets
+    // mono / stereo files of at least a second: time-chunked scan, every chunk on its own SM (loudness_scan.cu)
+    const bool file_path = tmp->d_scan_powers && tmp->force_kernel == 0 && h->force_kernel == 0 && n_buckets >= 10 &&
+                           scan_path_usable(tmp->lp, tmp->st, frames);
+    const size_t in_bytes = (len * sizeof(float) + 255) & ~(size_t)255;
+    const size_t stride = (size_t)n_buckets + 1;
+    rc = ensure_scratch_device(tmp, in_bytes + (file_path ? (size_t)channels * stride * sizeof(double) : 0));
     if (rc) return fail(h, rc, "calculate_integrated_lufs: %s", tmp->err);
     float* d = tmp->d_scratch;
     cudaError_t e = cudaMemcpyAsync(d, samples, len * sizeof(float), cudaMemcpyHostToDevice, tmp->stream);
-    for (size_t off = 0; off < len && !e && !rc; off += chunk) {
-      const size_t n = len - off < chunk ? len - off : chunk;
-      rc = feed_device(tmp, d + off, n / channels, n / channels);
-    }
     if (e) return cuda_fail(h, e, "calculate_integrated_lufs");
+    if (file_path) {
+      double* d_fb = reinterpret_cast<double*>(reinterpret_cast<char*>(tmp->d_scratch) + in_bytes);
+      // 1 s chunks (+0.4 s run-in) until the file outgrows four chunks per SM, then longer ones
+      size_t chunk_buckets = 10;
+      const size_t max_chunks = 4 * 148;
+      if ((n_buckets + chunk_buckets - 1) / chunk_buckets > max_chunks) chunk_buckets = (n_buckets + max_chunks - 1) / max_chunks;
+      e = launch_loudness_scan_file(tmp->lp, tmp->st, tmp->d_scan_powers, d, frames, d_fb, stride, chunk_buckets,
+                                    tmp->stream, &tmp->launches);
+      if (!e) e = launch_file_gating(tmp->gp, tmp->st, d_fb, stride, n_buckets, tmp->stream, &tmp->launches);
+      if (e) return cuda_fail(h, e, "calculate_integrated_lufs (file path)");
+      tmp->results_valid = false;   // total_frames stays 0: nothing is pending for the streaming gating
+    } else {
+      for (size_t off = 0; off < len && !rc; off += chunk) {
+        const size_t n = len - off < chunk ? len - off : chunk;
+        rc = feed_device(tmp, d + off, n / channels, n / channels);
+      }
+    }
   }
   if (!rc && ok) {
     double v = 0;

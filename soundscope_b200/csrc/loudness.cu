@@ -199,6 +199,49 @@ cudaError_t launch_gating(const GateParams& g, const LoudState& st, uint64_t j_f
   return cudaGetLastError();
 }
 
+// Whole-file gating: one thread per 100 ms hop of stream 0, bucket sums in a linear array (no ring).  Same summation
+// order as window_energy_t (oldest bucket first, channel by channel), so a block energy is the number k_gating computes.
+template <int NB>
+__device__ __forceinline__ double file_window_energy(const double* __restrict__ fb, size_t stride, const GateParams& g,
+                                                     uint64_t j) {
+  double sum = 0.0;
+  for (int c = 0; c < g.channels; c++) {
+    const float w = g.weight[c];
+    if (w == 0.0f) continue;
+    const double* b = fb + (size_t)c * stride + (j - (uint64_t)(NB - 1));
+    double ch = 0.0;
+#pragma unroll
+    for (int k = 0; k < NB; k++) ch += b[k];
+    if (w != 1.0f) ch *= 1.41;
+    sum += ch;
+  }
+  return sum / (double)((uint64_t)NB * g.s100);
+}
+
+__global__ void __launch_bounds__(128)
+k_file_gating(const GateParams g, const double* __restrict__ fb, size_t stride, uint64_t n_buckets,
+              const double* __restrict__ bounds, uint32_t* __restrict__ block_hist, uint32_t* __restrict__ st_hist) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_buckets) return;
+  if (g.do_i && j >= 3) {
+    const double e = file_window_energy<4>(fb, stride, g, j);
+    if (e >= bounds[0]) atomicAdd(&block_hist[find_histogram_index(bounds, e)], 1u);
+  }
+  if (g.do_lra && j >= 29 && (j - 29) % 10 == 0) {
+    const double e = file_window_energy<30>(fb, stride, g, j);
+    if (e >= bounds[0]) atomicAdd(&st_hist[find_histogram_index(bounds, e)], 1u);
+  }
+}
+
+cudaError_t launch_file_gating(const GateParams& g, const LoudState& st, const double* d_file_buckets, size_t bucket_stride,
+                               uint64_t n_buckets, cudaStream_t s, uint64_t* launches) {
+  if (!n_buckets || !(g.do_i || g.do_lra)) return cudaSuccess;
+  k_file_gating<<<(unsigned)((n_buckets + 127) / 128), 128, 0, s>>>(g, d_file_buckets, bucket_stride, n_buckets,
+                                                                    st.hist_boundaries, st.block_hist, st.st_hist);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // results: one warp per stream
 // ------------------------------------------------------------------------------------------------

@@ -25,6 +25,7 @@ namespace {
 constexpr int kScanLS = 64;        // frames per segment
 constexpr int kScanThreads = 256;
 constexpr int kMaxPow = 32;        // Pt^0 .. Pt^32 (mono: 32 segments per warp)
+constexpr int kFileWarmBuckets = 4;  // 0.4 s run-in of a file-mode chunk: |A^n| < e^-95 there at every sample rate
 
 struct ScanArgs {
   double na[5];
@@ -49,6 +50,11 @@ struct ScanArgs {
   unsigned slot0;
   int tp_factor;        // 0, 2, 4
   int do_sample_peak;
+  // file mode (whole-file one-shot, one stream): blockIdx.x is a time chunk instead of a stream
+  double* file_buckets;       // [C][file_bucket_stride] sum of y^2 per 100 ms bucket by GLOBAL bucket index; nullptr: streaming
+  size_t file_bucket_stride;
+  size_t chunk_frames;        // frames a CTA owns (multiple of s100)
+  size_t warm_frames;         // zero-state run-in before the owned range (multiple of s100)
 };
 
 __device__ __forceinline__ void to_diff(double v1, double v2, double v3, double v4, double& d0, double& d1,
@@ -87,7 +93,15 @@ k_loudness_scan(const __grid_constant__ ScanArgs a) {
   const int k = tid / C;                      // segment of the sweep
   const int c = tid - k * C;                  // channel
   const int kw = (lane / C);                  // segment index inside the warp
-  const size_t stream = blockIdx.x;
+  // File mode: the K-weighting poles sit at radius exp(-~240 / rate) per sample (the 38 Hz high-pass), so the state a
+  // chunk inherits from audio more than 0.4 s back is below 1e-40 of full scale: a CTA that starts `warm_frames`
+  // early from zero state reproduces the serial recursion to the last bit that matters, and the chunks of one file
+  // run on different SMs.  Only the owned buckets are written.
+  const bool file_mode = a.file_buckets != nullptr;
+  const size_t stream = file_mode ? 0 : blockIdx.x;
+  const size_t own0 = file_mode ? (size_t)blockIdx.x * a.chunk_frames : 0;
+  const size_t f_begin = (file_mode && own0 > a.warm_frames) ? own0 - a.warm_frames : 0;
+  const size_t f_end = file_mode ? (own0 + a.chunk_frames < a.frames ? own0 + a.chunk_frames : a.frames) : a.frames;
   const size_t gidx = stream * C + c;
   const bool live = (a.active_mask >> c) & 1ull;
   const float* x_base = a.in + stream * a.in_stride_frames * C + c;
@@ -95,21 +109,24 @@ k_loudness_scan(const __grid_constant__ ScanArgs a) {
   for (int i = tid; i < (kMaxPow + 1) * 16; i += kScanThreads) s_pow[i] = a.powers[i];
   if (k == 0) {
     const double* f = a.filt + gidx * 4;
-    s_carry[c][0] = live ? f[0] : 0.0; s_carry[c][1] = live ? f[1] : 0.0;
-    s_carry[c][2] = live ? f[2] : 0.0; s_carry[c][3] = live ? f[3] : 0.0;
+    const bool from_state = live && f_begin == 0;   // a run-in starts from zero state
+    s_carry[c][0] = from_state ? f[0] : 0.0; s_carry[c][1] = from_state ? f[1] : 0.0;
+    s_carry[c][2] = from_state ? f[2] : 0.0; s_carry[c][3] = from_state ? f[3] : 0.0;
   }
   // bucket bookkeeping lives in thread (k == 0, c)
   double acc_cur = 0.0;
   unsigned slot = a.slot0;
-  if (k == 0 && live && a.pos0 > 0) acc_cur = a.bucket[gidx * kNB + slot];
+  size_t gbucket = f_begin / a.s100;                 // file mode: global index of the bucket in progress
+  const size_t own_bucket0 = own0 / a.s100;
+  if (!file_mode && k == 0 && live && a.pos0 > 0) acc_cur = a.bucket[gidx * kNB + slot];
   float sp = 0.f, tp = 0.f;
   __syncthreads();
 
   const size_t sweep_frames = (size_t)NSEG * kScanLS;
-  unsigned pos_sweep = a.pos0;  // position of the sweep start inside the bucket in progress
-  for (size_t f0 = 0; f0 < a.frames; f0 += sweep_frames) {
+  unsigned pos_sweep = file_mode ? 0u : a.pos0;  // position of the sweep start inside the bucket in progress
+  for (size_t f0 = f_begin; f0 < f_end; f0 += sweep_frames) {
     const size_t seg0 = f0 + (size_t)k * kScanLS;
-    const int lv = seg0 >= a.frames ? 0 : (int)((a.frames - seg0) < (size_t)kScanLS ? (a.frames - seg0) : kScanLS);
+    const int lv = seg0 >= f_end ? 0 : (int)((f_end - seg0) < (size_t)kScanLS ? (f_end - seg0) : kScanLS);
     const float* xs = x_base + seg0 * C;
 
     // ---- pass 1: zero-state response of my segment ----
@@ -229,7 +246,7 @@ k_loudness_scan(const __grid_constant__ ScanArgs a) {
       }
     }
     // the last non-empty segment of the sweep owns the state carried to the next sweep / next call
-    const bool last_seg = lv > 0 && (seg0 + kScanLS >= a.frames || k == NSEG - 1);
+    const bool last_seg = lv > 0 && (seg0 + kScanLS >= f_end || k == NSEG - 1);
     __syncthreads();  // s_carry / s_warp / s_part of this sweep fully consumed / produced
     if (last_seg) { s_carry[c][0] = v1; s_carry[c][1] = v2; s_carry[c][2] = v3; s_carry[c][3] = v4; }
     // ---- fold the segment partials into the bucket ring, in time order ----
@@ -237,13 +254,18 @@ k_loudness_scan(const __grid_constant__ ScanArgs a) {
       unsigned p = pos_sweep;
       for (int j = 0; j < NSEG; j++) {
         const size_t sj = f0 + (size_t)j * kScanLS;
-        if (sj >= a.frames) break;
-        const unsigned lvj = (unsigned)((a.frames - sj) < (size_t)kScanLS ? (a.frames - sj) : kScanLS);
+        if (sj >= f_end) break;
+        const unsigned lvj = (unsigned)((f_end - sj) < (size_t)kScanLS ? (f_end - sj) : kScanLS);
         acc_cur += s_part[j][c][0];
         if (p + lvj >= a.s100) {   // the bucket in progress ends inside (or at the end of) this segment
-          if (live) a.bucket[gidx * kNB + slot] = acc_cur;
+          if (file_mode) {
+            if (gbucket >= own_bucket0) a.file_buckets[(size_t)c * a.file_bucket_stride + gbucket] = live ? acc_cur : 0.0;
+            ++gbucket;
+          } else {
+            if (live) a.bucket[gidx * kNB + slot] = acc_cur;
+            slot = (slot + 1) % kNB;
+          }
           acc_cur = s_part[j][c][1];
-          slot = (slot + 1) % kNB;
           p = p + lvj - a.s100;
         } else {
           p += lvj;
@@ -255,6 +277,7 @@ k_loudness_scan(const __grid_constant__ ScanArgs a) {
   }
 
   // ---------------- epilogue ----------------
+  if (file_mode) return;   // the one-shot meter keeps nothing but the bucket energies (an unfinished bucket is never gated)
   s_pk[0][tid] = sp;
   s_pk[1][tid] = tp;
   __syncthreads();
@@ -324,6 +347,42 @@ cudaError_t launch_loudness_scan(const LoudParams& p, const LoudState& st, const
   a.do_sample_peak = p.do_sample_peak;
   if (p.channels == 1) k_loudness_scan<1><<<(unsigned)st.n_streams, kScanThreads, 0, s>>>(a);
   else k_loudness_scan<2><<<(unsigned)st.n_streams, kScanThreads, 0, s>>>(a);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// Whole-file one-shot (Analyzer::calculate_integrated_lufs, analyzer.rs:170-182): one stream starting at the meter's
+// reset state, split into time chunks of `chunk_buckets` 100 ms buckets, one CTA each, every chunk but the first
+// preceded by a zero-state run-in of kFileWarmBuckets buckets.  Fills d_file_buckets[C][stride] with the energy sums of
+// every COMPLETE bucket; the caller gates them (launch_file_gating).
+cudaError_t launch_loudness_scan_file(const LoudParams& p, const LoudState& st, const double* d_powers, const float* d_in,
+                                      size_t frames, double* d_file_buckets, size_t bucket_stride, size_t chunk_buckets,
+                                      cudaStream_t s, uint64_t* launches) {
+  if (!frames) return cudaSuccess;
+  ScanArgs a{};
+  memcpy(a.na, p.na, sizeof(a.na));
+  memcpy(a.b, p.b, sizeof(a.b));
+  a.in = d_in;
+  a.powers = d_powers;
+  a.filt = st.filt;
+  a.bucket = st.bucket;
+  a.speak = st.speak;
+  a.tpeak = st.tpeak;
+  a.tphist = st.tphist;
+  a.ring = nullptr;
+  a.in_stride_frames = frames;
+  a.frames = frames;
+  a.active_mask = p.do_filter ? p.active_mask : 0;
+  a.s100 = p.s100;
+  a.tp_factor = 0;         // only the integrated loudness leaves the one-shot meter
+  a.do_sample_peak = 0;
+  a.file_buckets = d_file_buckets;
+  a.file_bucket_stride = bucket_stride;
+  a.chunk_frames = chunk_buckets * (size_t)p.s100;
+  a.warm_frames = (size_t)kFileWarmBuckets * p.s100;
+  const size_t n_chunks = (frames + a.chunk_frames - 1) / a.chunk_frames;
+  if (p.channels == 1) k_loudness_scan<1><<<(unsigned)n_chunks, kScanThreads, 0, s>>>(a);
+  else k_loudness_scan<2><<<(unsigned)n_chunks, kScanThreads, 0, s>>>(a);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -92,7 +92,8 @@ struct DeviceGuard {
 
 // capi.cu
 int32_t ensure_stage(ssb_analyzer* h, size_t floats);
-int32_t ensure_scratch(ssb_analyzer* h, size_t bytes);
+int32_t ensure_scratch(ssb_analyzer* h, size_t bytes);          // device scratch + pinned host mirror of the same size
+int32_t ensure_scratch_device(ssb_analyzer* h, size_t bytes);   // device scratch only
 // feed `frames` frames per stream from device memory laid out [stream][in_stride_frames][C]
 int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in_stride_frames);
 int32_t get_plan(ssb_analyzer* h, size_t n, uint32_t rate, FftPlan** out);

@@ -92,6 +92,13 @@ bool scan_path_usable(const LoudParams& p, const LoudState& st, size_t frames);
 cudaError_t launch_loudness_scan(const LoudParams& p, const LoudState& st, const double* d_powers, const float* d_in,
                                  size_t frames, size_t in_stride_frames, uint32_t pos0, uint64_t bucket0,
                                  size_t ring_pos, cudaStream_t s, uint64_t* launches);
+// Whole-file one-shot: time-chunked scan of ONE stream from the reset state into d_file_buckets[C][bucket_stride]
+// (energy sum of every complete 100 ms bucket by global index), then gating of all its blocks into the histograms.
+cudaError_t launch_loudness_scan_file(const LoudParams& p, const LoudState& st, const double* d_powers, const float* d_in,
+                                      size_t frames, double* d_file_buckets, size_t bucket_stride, size_t chunk_buckets,
+                                      cudaStream_t s, uint64_t* launches);
+cudaError_t launch_file_gating(const GateParams& g, const LoudState& st, const double* d_file_buckets, size_t bucket_stride,
+                               uint64_t n_buckets, cudaStream_t s, uint64_t* launches);
 // Gating for buckets [j_first, j_last] completed by the preceding filter launch.
 cudaError_t launch_gating(const GateParams& g, const LoudState& st, uint64_t j_first, uint64_t j_last,
                           cudaStream_t s, uint64_t* launches);

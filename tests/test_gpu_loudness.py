@@ -380,3 +380,41 @@ def test_rows_any_even_split_matches_generic(ssb, cuda, n, channels, rate):
     assert np.array_equal(a, b, equal_nan=True)
     for s in (0, n // 2, n - 1):
         assert np.array_equal(fast.histograms(s)[0], slow.histograms(s)[0])
+
+
+@pytest.mark.parametrize("channels,rate,seconds", [(2, 48000, 63.7), (1, 44100, 30.0), (2, 96000, 12.3), (2, 44100, 1.05),
+                                                   (2, 48000, 0.95), (2, 22050, 41.0), (2, 48000, 301.0)])
+def test_one_shot_time_chunked_matches_streaming_and_oracle(ssb, oracle, cuda, channels, rate, seconds):
+    """calculate_integrated_lufs runs the file as time chunks on different SMs, each from a 0.4 s zero-state run-in
+    (loudness_scan.cu, file mode): same integrated loudness as the oracle's serial pass over the whole file (1e-9 LU: the
+    same 400 ms blocks fall in the same histogram bins) and as this library's own streaming meter fed the same chunks."""
+    rng = np.random.default_rng(int(seconds * 10) + channels)
+    n = int(rate * seconds)
+    t = np.arange(n) / rate
+    env = 0.05 + 0.45 * (0.5 + 0.5 * np.sin(2 * np.pi * t / 7.3)) * (np.floor(t / 3.1) % 3 != 1)   # loud / quiet / gated stretches
+    x = (env[:, None] * np.sin(2 * np.pi * 330.0 * t)[:, None] * np.linspace(1.0, 0.6, channels)[None, :]
+         + 0.01 * rng.standard_normal((n, channels))).astype(np.float32).ravel()
+    a, o = ssb.Analyzer(), oracle.Analyzer()
+    a.create_loudness_meter(2, rate)           # calculate_integrated_lufs takes its rate from the analyzer, channels from the call
+    o.create_loudness_meter(2, rate)
+    got, want = a.calculate_integrated_lufs(channels, x), o.calculate_integrated_lufs(channels, x)
+    assert (got is None) == (want is None)
+    if np.isfinite(want):
+        assert abs(got - want) <= 1e-9, (got, want)
+    else:
+        assert got == want
+    s = ssb.BatchAnalyzer(1, channels, rate, ssb.MODE_I | ssb.MODE_HISTOGRAM)     # streaming meter, same chunking
+    step = rate * 2
+    for off in range(0, x.size, step):
+        s.add_frames_host(x[off:off + step].reshape(1, -1, channels))
+    assert s.loudness_global()[0] == got or abs(s.loudness_global()[0] - got) <= 1e-9
+
+
+def test_one_shot_silence_and_dc_steps(ssb, oracle, cuda):
+    a, o = ssb.Analyzer(), oracle.Analyzer()
+    a.create_loudness_meter(2, 48000)
+    o.create_loudness_meter(2, 48000)
+    z = np.zeros(48000 * 2 * 20, dtype=np.float32)
+    assert a.calculate_integrated_lufs(2, z) == -np.inf
+    z[48000 * 2 * 13:48000 * 2 * 14] = 0.5          # one second of DC inside silence: the high-pass tail crosses a chunk boundary
+    assert abs(a.calculate_integrated_lufs(2, z) - o.calculate_integrated_lufs(2, z)) <= 1e-9
