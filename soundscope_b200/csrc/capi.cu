@@ -575,8 +575,9 @@ int32_t ssb_results_device(ssb_analyzer* h, double* d_out) {
   return SSB_OK;
 }
 
-int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const float* samples, size_t len,
-                                      double* out, int32_t* is_some) {
+// `d_resident`: the same samples already on the device (complete, any stream), or nullptr to copy them from `samples`
+static int32_t one_shot_integrated(ssb_analyzer* h, uint32_t channels, const float* samples, const float* d_resident,
+                                   size_t len, double* out, int32_t* is_some) {
   if (!h || !out || !is_some || (!samples && len)) return SSB_ERR_INVALID_ARG;
   *is_some = 0;
   DeviceGuard g(h->device);
@@ -616,13 +617,18 @@ int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const 
                            scan_path_usable(tmp->lp, tmp->st, frames);
     const size_t in_bytes = (len * sizeof(float) + 255) & ~(size_t)255;
     const size_t stride = (size_t)n_buckets + 1;
-    rc = ensure_scratch_device(tmp, in_bytes + (file_path ? (size_t)channels * stride * sizeof(double) : 0));
+    const size_t own_in = d_resident ? 0 : in_bytes;
+    rc = ensure_scratch_device(tmp, own_in + (file_path ? (size_t)channels * stride * sizeof(double) : 0) + 256);
     if (rc) return fail(h, rc, "calculate_integrated_lufs: %s", tmp->err);
-    float* d = tmp->d_scratch;
-    cudaError_t e = cudaMemcpyAsync(d, samples, len * sizeof(float), cudaMemcpyHostToDevice, tmp->stream);
+    const float* d = d_resident;
+    cudaError_t e = cudaSuccess;
+    if (!d_resident) {
+      e = cudaMemcpyAsync(tmp->d_scratch, samples, len * sizeof(float), cudaMemcpyHostToDevice, tmp->stream);
+      d = tmp->d_scratch;
+    }
     if (e) return cuda_fail(h, e, "calculate_integrated_lufs");
     if (file_path) {
-      double* d_fb = reinterpret_cast<double*>(reinterpret_cast<char*>(tmp->d_scratch) + in_bytes);
+      double* d_fb = reinterpret_cast<double*>(reinterpret_cast<char*>(tmp->d_scratch) + own_in);
       // 1 s chunks (+0.4 s run-in) until the file outgrows four chunks per SM, then longer ones
       size_t chunk_buckets = 10;
       const size_t max_chunks = 4 * 148;
@@ -646,6 +652,11 @@ int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const 
   }
   h->launches += tmp->launches - launches0;
   return rc;
+}
+
+int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const float* samples, size_t len,
+                                      double* out, int32_t* is_some) {
+  return one_shot_integrated(h, channels, samples, nullptr, len, out, is_some);
 }
 
 int32_t ssb_fft_bins(size_t n, uint32_t rate, size_t* k_first, size_t* n_bins) {
@@ -853,8 +864,9 @@ int32_t ssb_preanalyze_file(ssb_analyzer* h, const float* samples, size_t len, u
   const int32_t meter_rc = ssb_create_loudness_meter(h, 2, rate);
   (void)meter_rc;
   // tui.rs:1229: integrated loudness of the file, channels hard-coded to 2.  The samples are already in the
-  // handle's device scratch (ssb_get_waveform put them there): feed the one-shot meter from it.
-  return ssb_calculate_integrated_lufs(h, 2, samples, len, integrated, is_some);
+  // handle's device scratch (ssb_get_waveform put them there and synchronised): the one-shot meter reads that copy.
+  const bool resident = n_points && *n_points > 0 && h->d_scratch && h->scratch_cap >= len * sizeof(float);
+  return one_shot_integrated(h, 2, samples, resident ? h->d_scratch : nullptr, len, integrated, is_some);
 }
 
 int32_t ssb_mid_side_device(ssb_analyzer* h, const float* d_interleaved, size_t len, float* d_mid, float* d_side) {
