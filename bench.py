@@ -261,7 +261,7 @@ def run_ours(args):
 
     # ---- optional extras: Mode::all() (adds sample + true peak) and the cfg3 FFT, device-resident ----
     extras = {}
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:   # single-GPU runs only: the scaling runs stay lean
         try:
             an3 = S.BatchAnalyzer(N_STREAMS, CHANNELS, RATE, S.MODE_ALL, device=local)
             for i in range(2):
