@@ -27,7 +27,7 @@ SSB_HD unsigned fft_pad(unsigned p) { return p + (p >> 5) + (p >> 9); }
 // Complex add / subtract are the bulk of a butterfly.  On sm_100 both halves go through one packed FP32 instruction
 // (FADD2; a - b as FFMA2 b * (-1, -1) + a, exact), halving the issue slots of an issue-bound kernel; the host build
 // (tests/test_fft_core_host.py) and SSB_FFT_SCALAR keep the scalar form — same IEEE results either way.
-#if defined(__CUDA_ARCH__) && !defined(SSB_FFT_SCALAR)
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000 && !defined(SSB_FFT_SCALAR)
 SSB_HD float2 c_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
 SSB_HD float2 c_sub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
 #else
