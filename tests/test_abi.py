@@ -77,3 +77,34 @@ def test_fft_axis_matches_oracle(ssb, oracle):
         assert m.value == nb
         ref = oracle.get_fft(ref_sine_f32(1000.0, n, rate), rate)
         assert np.array_equal(x, ref[:, 0])  # chart x depends only on (n, rate): bit-exact
+
+
+def test_capture_entry_points_without_device(ssb):
+    """stateless parts of the capture ABI work anywhere; anything that needs memory fails loudly without a device"""
+    import torch
+    L = ssb.lib()
+    sizes = {"u8": 1, "s8": 1, "s16le": 2, "s16be": 2, "s24le": 3, "s24be": 3, "s32le": 4, "s32be": 4,
+             "f32le": 4, "f32be": 4, "f64le": 8, "f64be": 8}
+    for name, code in ssb.PCM_FORMATS.items():
+        assert L.ssb_pcm_bytes_per_sample(code) == sizes[name]
+    assert L.ssb_pcm_bytes_per_sample(99) == 0 and L.ssb_pcm_bytes_per_sample(-1) == 0
+    if not torch.cuda.is_available():
+        with pytest.raises(ssb.SsbError) as e:
+            ssb.CaptureRing(1000)
+        assert e.value.code == 13  # SSB_ERR_NO_DEVICE: the ring is pinned + device memory, there is no host-only ring
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle on the host cores) prints one JSON line with the contract's keys;
+    it needs no GPU, so the driver-facing format is checked here."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "cfg2" in line["config"]["workload"] and line["vs_baseline"] is None and line["gpu_launches"] == 0
