@@ -35,3 +35,9 @@ for i in range(3):
     ring.push(np.random.default_rng(7 + i).uniform(-0.5, 0.5, 768).astype(np.float32))
     single.analyze_microphone_input(ring)
 print("done")
+# whole-file one-shot (file-mode k_loudness_scan + k_file_gating) on a 60 s stereo file
+from tests.signals import sweep_stereo
+whole = np.tile(sweep_stereo(10.0, 48000), 6)
+for i in range(2):
+    single.calculate_integrated_lufs(2, whole)
+print("done one-shot")
