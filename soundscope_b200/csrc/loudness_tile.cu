@@ -652,14 +652,15 @@ k_loudness_rows(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 // tile 32 frames (32*C floats per stream = exactly C lines, so every C is supported).
 // ------------------------------------------------------------------------------------------------
 constexpr int kAnyF = 32;
-constexpr int kAnyWarps = 8;
+constexpr int kAnyWarps = 8;        // compute warps per CTA without the true-peak FIR (3 CTAs per SM)
+constexpr int kAnyWarpsTp = 15;     // with it: one CTA of 15 + 1 warps (512 threads) per SM, 128 registers per thread
 
 // NS TMA stages of 32 KB, MINB CTAs per SM: without the true-peak FIR the kernel is latency-bound (one dependent
 // recursion per lane), so it trades a stage for a third resident CTA (24 compute warps per SM)
-template <int TPF, int NS, int MINB>
-__global__ void __launch_bounds__(kAnyWarps * 32 + 32, MINB)
+template <int TPF, int NS, int MINB, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32 + 32, MINB)
 k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileArgs a, const int C,
-                    const int ROWS) {   // ROWS: streams per TMA box (multiple of 8, <= kAnyWarps * RW), >= what a CTA owns
+                    const int ROWS) {   // ROWS: streams per TMA box (multiple of 8, <= NWARPS * RW), >= what a CTA owns
   constexpr int F = kAnyF;
   const int RW = 32 / C;                 // streams per warp
   const unsigned STAGE_BYTES = (unsigned)C * ROWS * 128u;
@@ -667,7 +668,8 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stages = smem;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * 32768);  // stage <= 32 KB for every C
+  constexpr unsigned SLOT = NWARPS * 4096u;   // bytes reserved per stage: NWARPS * RW rows x C lines x 128 B <= NWARPS * 4 KB
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * SLOT);
   uint64_t* empty = full + NS;
 
   const int tid = threadIdx.x;
@@ -688,13 +690,13 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
   }
   __syncthreads();
 
-  if (warp == kAnyWarps) {
+  if (warp == NWARPS) {
     if (lane == 0 && live_warps > 0) {
       for (unsigned tile = 0; tile < a.n_tiles; tile++) {
         const unsigned s = tile % NS;
         if (tile >= (unsigned)NS) mbar_wait(&empty[s], ((tile / NS) - 1) & 1);
         mbar_expect_tx(&full[s], STAGE_BYTES);
-        tma_load_3d(stages + (size_t)s * 32768, &tmap, &full[s], 0, (int)row0, (int)(tile * C));
+        tma_load_3d(stages + (size_t)s * SLOT, &tmap, &full[s], 0, (int)row0, (int)(tile * C));
       }
     }
     return;
@@ -724,12 +726,12 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
   for (int t = 0; t < TPW; t++) w[t] = (TPF != 0 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
   unsigned pos = a.pos0;
 
-  // Where this lane's 32 samples of a tile sit inside a stage (swizzled): it depends on (row, channel) only, so the
-  // loudness-only variant keeps the byte offsets in registers, two 16-bit offsets per register (a stage is <= 32 KB),
-  // and the recursion loop spends one extract instead of ~8 address instructions per sample.  The true-peak
-  // variants have no registers to spare (3 CTAs x 288 threads leave 72 per thread) and compute the address.
-  constexpr bool kPackedOffsets = TPF == 0;
-  unsigned offp[kPackedOffsets ? F / 2 : 1];
+  // Where this lane's 32 samples of a tile sit inside a stage (swizzled) depends on (row, channel) only: the byte
+  // offsets live in registers, two 16-bit offsets per register (a stage is <= 64 KB), and the fully unrolled tile loop
+  // spends one extract instead of ~8 address instructions per sample; full unrolling also turns the true-peak
+  // window shift into register renaming (23 moves per tile instead of per 4 samples).
+  constexpr bool kPackedOffsets = true;
+  unsigned offp[F / 2];
   if (kPackedOffsets) {
 #pragma unroll
     for (int j = 0; j < F / 2; j++) {
@@ -747,7 +749,7 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
   for (unsigned tile = 0; tile < a.n_tiles; tile++) {
     const unsigned s = tile % NS;
     mbar_wait_warp(&full[s], (tile / NS) & 1);
-    const unsigned char* stage_base = stages + (size_t)s * 32768;
+    const unsigned char* stage_base = stages + (size_t)s * SLOT;
     const unsigned char* row_base = stage_base + (size_t)(lane_ok ? r : 0) * 128;
     const unsigned to_boundary = a.s100 - pos;
     // one sample of this lane's channel: peaks, K-weighting step, y^2 into the bucket in progress
@@ -781,13 +783,8 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
     }
     if (to_boundary > (unsigned)F) {
       // the usual tile (299 of 300 at 96 kHz): no bucket ends inside it, the loop carries no boundary test
-      if (kPackedOffsets) {
 #pragma unroll
-        for (int f = 0; f < F; f++) SSB_ANY_SAMPLE(f, SSB_ANY_LOAD_PACKED)
-      } else {
-#pragma unroll 4
-        for (int f = 0; f < F; f++) SSB_ANY_SAMPLE(f, SSB_ANY_LOAD_CALC)
-      }
+      for (int f = 0; f < F; f++) SSB_ANY_SAMPLE(f, SSB_ANY_LOAD_PACKED)
     } else {
 #pragma unroll 1
       for (int f = 0; f < F; f++) {
@@ -951,11 +948,11 @@ cudaError_t launch_rows_c(const CUtensorMap& tmap, const TileArgs& args, unsigne
 }
 
 
-template <int TPF, int NS, int MINB>
+template <int TPF, int NS, int MINB, int NWARPS>
 cudaError_t launch_any_cfg(const CUtensorMap& tmap, const TileArgs& args, unsigned n_ctas, int C, int box_rows,
                            cudaStream_t s) {
-  auto kern = k_loudness_rows_any<TPF, NS, MINB>;
-  const size_t smem = (size_t)NS * 32768 + 2 * NS * sizeof(uint64_t) + 1024;
+  auto kern = k_loudness_rows_any<TPF, NS, MINB, NWARPS>;
+  const size_t smem = (size_t)NS * NWARPS * 4096 + 2 * NS * sizeof(uint64_t) + 1024;
   static bool configured_dev[64] = {false};
   int dev_ = 0;
   cudaGetDevice(&dev_);
@@ -965,7 +962,7 @@ cudaError_t launch_any_cfg(const CUtensorMap& tmap, const TileArgs& args, unsign
     if (e) return e;
     configured = true;
   }
-  kern<<<n_ctas, kAnyWarps * 32 + 32, smem, s>>>(tmap, args, C, box_rows);
+  kern<<<n_ctas, NWARPS * 32 + 32, smem, s>>>(tmap, args, C, box_rows);
   return cudaGetLastError();
 }
 
@@ -1018,14 +1015,16 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  int box_rows = any_c ? kAnyWarps * (32 / C) : (serial ? kRowsSerial : kRows);
+  const bool any_tp = p.do_true_peak && p.tp_factor;
+  // multichannel kernel: a box holds whole warps' worth of streams, rounded down to the swizzle period of 8 rows
+  int box_rows = any_c ? (any_tp ? kAnyWarpsTp : kAnyWarps) * (32 / C) / 8 * 8 : (serial ? kRowsSerial : kRows);
   size_t any_ctas = 0;
   if (any_c) {
-    // three (two with the true-peak FIR) CTAs fit an SM: the grid is the smallest multiple of the resident slots that
+    // three CTAs of 8 warps (one of 16 warps with the true-peak FIR) fit an SM: the grid is the smallest multiple of the resident slots that
     // keeps <= box_rows streams per CTA, so every SM carries the same number of streams (few streams: one CTA per
     // box), and the TMA box shrinks to what a CTA owns
     any_ctas = (st.n_streams + box_rows - 1) / box_rows;
-    const size_t slots = (size_t)((p.do_true_peak && p.tp_factor) ? 2 : 3) * (size_t)sms;
+    const size_t slots = (size_t)(any_tp ? 1 : 3) * (size_t)sms;
     if (st.n_streams >= slots) {
       any_ctas = (any_ctas + slots - 1) / slots * slots;
     }
@@ -1074,9 +1073,9 @@ cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const
   cudaError_t e;
   if (any_c) {
     const size_t n_ctas = any_ctas;
-    e = tpf == 4 ? launch_any_cfg<4, 3, 2>(tmap, a, (unsigned)n_ctas, C, box_rows, s)
-                 : (tpf == 2 ? launch_any_cfg<2, 3, 2>(tmap, a, (unsigned)n_ctas, C, box_rows, s)
-                             : launch_any_cfg<0, 2, 3>(tmap, a, (unsigned)n_ctas, C, box_rows, s));
+    e = tpf == 4 ? launch_any_cfg<4, 3, 1, kAnyWarpsTp>(tmap, a, (unsigned)n_ctas, C, box_rows, s)
+                 : (tpf == 2 ? launch_any_cfg<2, 3, 1, kAnyWarpsTp>(tmap, a, (unsigned)n_ctas, C, box_rows, s)
+                             : launch_any_cfg<0, 2, 3, kAnyWarps>(tmap, a, (unsigned)n_ctas, C, box_rows, s));
   } else if (serial) {
     const size_t n_ctas = (st.n_streams + kRowsSerial - 1) / kRowsSerial;
     e = C == 1 ? launch_rows_c<1>(tmap, a, (unsigned)n_ctas, tpf, s) : launch_rows_c<2>(tmap, a, (unsigned)n_ctas, tpf, s);
