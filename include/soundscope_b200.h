@@ -125,8 +125,11 @@ int32_t ssb_get_true_peak(ssb_analyzer* h, double* left, double* right);
  * the multi-GPU gather moves.  Asynchronous. */
 size_t ssb_result_stride(const ssb_analyzer* h);
 int32_t ssb_results_device(ssb_analyzer* h, double* d_out);
-/* Analyzer::calculate_integrated_lufs (analyzer.rs:170-182): fresh Mode::all() meter at the handle's
- * rate, fed in chunks of sample_rate*2 samples.  *is_some = 0 mirrors `None`. */
+/* Analyzer::calculate_integrated_lufs (analyzer.rs:170-182): a fresh meter at the handle's rate over the whole
+ * interleaved file; a `sample_rate*2`-sample chunk that is not whole frames (or an invalid channel count) gives
+ * *is_some = 0, the reference's `None`.  The reference builds the meter with Mode::all() but reads nothing except
+ * loudness_global(), so only K-weighting and gating run here; mono / stereo files of a second or more are cut into
+ * time chunks that run on different SMs (each from a 0.4 s zero-state run-in, exact to the last bit of an f64 state). */
 int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const float* samples,
                                       size_t len, double* out, int32_t* is_some);
 
