@@ -108,3 +108,34 @@ def test_bench_reference_arm_contract():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "cfg2" in line["config"]["workload"] and line["vs_baseline"] is None and line["gpu_launches"] == 0
+
+
+def test_header_is_plain_c_and_links_from_c(ssb):
+    """the boundary is a C ABI: include/soundscope_b200.h compiles with gcc -std=c11 -pedantic and a C program links
+    against the shared library (create fails loudly with SSB_ERR_NO_DEVICE when there is no GPU)"""
+    import subprocess
+    import tempfile
+    import torch
+    prog = r'''
+#include "soundscope_b200.h"
+#include <stdio.h>
+int main(void) {
+  ssb_analyzer* h = NULL;
+  ssb_capture_ring* r = NULL;
+  int32_t rc = ssb_analyzer_create(&h, 2, 44100, SSB_MODE_ALL, 1, -1, SSB_FLAG_RING);
+  int32_t rr = ssb_capture_ring_create(&r, 1000, -1);
+  printf("%d %d %u %zu\n", rc, rr, ssb_abi_version(), ssb_pcm_bytes_per_sample(SSB_PCM_S24LE));
+  if (rc == SSB_OK) ssb_analyzer_destroy(h);
+  if (rr == SSB_OK) ssb_capture_ring_destroy(r);
+  return rc * 100 + rr;
+}
+'''
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "t.c"), os.path.join(d, "t")
+        open(src, "w").write(prog)
+        libdir = os.path.dirname(ssb.library_path())
+        subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                               src, "-o", exe, "-L", libdir, "-lsoundscope_b200", f"-Wl,-rpath,{libdir}"])
+        r = subprocess.run([exe], capture_output=True, text=True)
+        want = 0 if torch.cuda.is_available() else 13 * 100 + 13
+        assert r.returncode == want % 256, r.stdout + r.stderr
