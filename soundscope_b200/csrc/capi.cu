@@ -750,6 +750,7 @@ int32_t ssb_process_tick(ssb_analyzer* h, const float* tail, size_t n_fft, size_
                          int32_t* lufs_status) {
   if (!h || !tail || !n_points || !shortterm_lufs || !fft_status || !lufs_status) return SSB_ERR_INVALID_ARG;
   if (h->channels != 2 || h->n_streams != 1) return fail(h, SSB_ERR_INVALID_ARG, "process_tick needs one stereo stream");
+  if (!h->meter_ok) return fail(h, SSB_ERR_NOMEM, "the loudness meter is not initialised (a previous create/reinit failed)");
   if (lufs_samples > 2 * n_fft) return fail(h, SSB_ERR_INVALID_ARG, "lufs_samples exceeds the tail");
   *n_points = 0;
   *fft_status = fft_shape_check(n_fft, h->rate);

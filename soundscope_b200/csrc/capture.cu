@@ -469,6 +469,7 @@ int32_t ssb_mic_tick(ssb_analyzer* h, ssb_capture_ring* ring, size_t n_fft, size
   if (!h || !ring || !n_points || !n_wave_points || !shortterm_lufs || !fft_status || !lufs_status)
     return SSB_ERR_INVALID_ARG;
   if (h->n_streams != 1) return fail(h, SSB_ERR_INVALID_ARG, "mic_tick needs a one-stream handle");
+  if (!h->meter_ok) return fail(h, SSB_ERR_NOMEM, "the loudness meter is not initialised (a previous create/reinit failed)");
   if (ring->device != h->device) return fail(h, SSB_ERR_INVALID_ARG, "ring and analyzer live on different devices");
   *n_points = 0;
   *n_wave_points = 0;
