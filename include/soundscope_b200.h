@@ -129,7 +129,8 @@ int32_t ssb_results_device(ssb_analyzer* h, double* d_out);
  * interleaved file; a `sample_rate*2`-sample chunk that is not whole frames (or an invalid channel count) gives
  * *is_some = 0, the reference's `None`.  The reference builds the meter with Mode::all() but reads nothing except
  * loudness_global(), so only K-weighting and gating run here; mono / stereo files of a second or more are cut into
- * time chunks that run on different SMs (each from a 0.4 s zero-state run-in, exact to the last bit of an f64 state). */
+ * time chunks that run on different SMs (each from a 0.4 s zero-state run-in: the inherited state has decayed by e^-95,
+ * block energies agree with the serial pass to the recursion's rounding noise, < 1e-8 LU). */
 int32_t ssb_calculate_integrated_lufs(ssb_analyzer* h, uint32_t channels, const float* samples,
                                       size_t len, double* out, int32_t* is_some);
 
