@@ -34,3 +34,23 @@ def stream_batch(n_streams, frames, channels, seed=0x5EED, rate=48000, t0=0):
     x = 0.25 * np.sin(2 * np.pi * f[:, None, None] * t[None, :, None] + ph[:, None, :])
     x += 0.05 * rng.uniform(-1, 1, size=(n_streams, frames, channels))
     return x.astype(np.float32)
+
+
+def ref_mic_test_ring_fill(sr):
+    """The reference's microphone-tick tests (tui.rs:2271-2368) fill the ring with
+    `(i as f32 * 500.0 * 2.0 * PI / sr as f32).sin()` for i in 0..sr*30 — f32 arithmetic throughout."""
+    i = np.arange(sr * 30, dtype=np.float32)
+    ph = (i * np.float32(500.0) * np.float32(2.0) * np.float32(np.pi) / np.float32(sr)).astype(np.float32)
+    return np.sin(ph).astype(np.float32)
+
+
+def ref_mic_test_assertions(sr, mid_fft):
+    """tui.rs:2289-2302 (and the 48000 / 96000 copies): the spectrum is non-empty and the point at
+    round(500 / (sr / 2) * len) reads below -20 dB."""
+    assert mid_fft is not None and len(mid_fft) > 0
+    freq_bin = np.float32(500.0) / (np.float32(sr) / np.float32(2.0)) * np.float32(len(mid_fft))
+    bin_idx = int(np.round(freq_bin))
+    assert bin_idx < len(mid_fft), f"Bin index out of range: {bin_idx}"
+    amp = mid_fft[bin_idx][1]
+    assert amp < -20.0, f"Expected strong signal at ~500Hz, got: {amp}"
+    return bin_idx, amp

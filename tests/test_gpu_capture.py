@@ -293,3 +293,18 @@ def test_capture_ring_concurrent_producer_snapshots_are_consistent(ssb, cuda):
         stop.set()
         t.join()
     assert good > 0
+
+
+@pytest.mark.parametrize("sr", [44100, 48000, 96000])
+def test_reference_mic_tests_on_gpu(ssb, oracle, cuda, sr):
+    """The reference's own microphone-tick tests (tui.rs:2271-2368) through the C ABI: a 44100 * 30 ring (tui.rs:2200),
+    the default analyzer, sr * 30 enqueued sine samples; the reference's assertions, then parity with the oracle."""
+    from tests.signals import ref_mic_test_assertions, ref_mic_test_ring_fill
+    s = ref_mic_test_ring_fill(sr)
+    ring, oref = ssb.CaptureRing(44100 * 30), oracle.capture_ref.RingRef(44100 * 30)
+    ring.push(s)
+    oref.callback(s, False)
+    a, o = ssb.Analyzer(), oracle.Analyzer()
+    got = a.analyze_microphone_input(ring)
+    ref_mic_test_assertions(sr, got[0])
+    _check_tick(got, oracle.capture_ref.mic_tick(oref.to_vec(), o))

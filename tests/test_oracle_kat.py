@@ -433,3 +433,16 @@ def test_oracle_true_peak_against_polyphase_resampler(oracle):
     m.add_frames_f32(tone)
     assert abs(m.sample_peak(0) - 0.5 / np.sqrt(2)) < 1e-6
     assert -0.4 <= 20 * np.log10(m.true_peak(0) / 0.5) <= 0.2          # EBU Tech 3341's true-peak tolerance
+
+
+@pytest.mark.parametrize("sr", [44100, 48000, 96000])
+def test_ref_analyze_microphone_input(oracle, sr):
+    """The reference's own microphone-tick tests (tui.rs:2271-2368) on the oracle: `create_test_app` gives a ring of
+    44100 * 30 values (tui.rs:2200) and a default (2 ch, 44100 Hz) device analyzer; the test enqueues sr * 30 samples of
+    a sine and calls analyze_microphone_input()."""
+    from tests.signals import ref_mic_test_assertions, ref_mic_test_ring_fill
+    ring = oracle.capture_ref.RingRef(44100 * 30)
+    ring.callback(ref_mic_test_ring_fill(sr), False)          # buffer.clear(); buffer.enqueue(sample) x sr*30: ends full
+    mid, side, wave, st, err = oracle.capture_ref.mic_tick(ring.to_vec(), oracle.Analyzer())
+    ref_mic_test_assertions(sr, mid)
+    assert err is None and mid.shape == (7423, 2) and wave.shape == (30000, 2) and np.isfinite(st)
