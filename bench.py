@@ -495,7 +495,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)  # 2000 x 0.25 ms: a 0.5 s timed region, several nvidia-smi clock samples inside it
+    ap.add_argument("--steps", type=int, default=200)  # 200 x 0.25 ms = 50 ms timed region
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
