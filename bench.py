@@ -75,27 +75,67 @@ def make_input_device_chunked(torch, n_streams, frames, seed, device, chunk=4096
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe).  Rows carry nvidia-smi's
+    own timestamp, so the ones that fall inside [mark_begin, mark_end] are told apart from the idle ones around it
+    whatever the pipe buffering; the median is taken over the in-region rows when there are any."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        import datetime
+        self.t_begin = datetime.datetime.now()
+
+    def mark_end(self):
+        import datetime
+        self.t_end = datetime.datetime.now()
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
+
+    @staticmethod
+    def parse_row(r):
+        """-> (timestamp or None, sm_mhz, sm_max_mhz, [reason names]) or None for a malformed row"""
+        import datetime
+        p = [c.strip() for c in r.split(",")]
+        if len(p) < 10:
+            return None
+        try:
+            sm, mx = float(p[2]), float(p[3])
+        except ValueError:
+            return None
+        try:
+            ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f")
+        except ValueError:
+            ts = None
+        reasons = [nm for nm, v in zip(ClockSampler.NAMES, p[6:10]) if v.lower().startswith("active")]
+        return ts, sm, mx, reasons
+
+    def summarise(self):
+        parsed = [q for q in (self.parse_row(r) for r in self.rows) if q is not None]
+        inside = [q for q in parsed if q[0] is not None and self.t_begin is not None and self.t_end is not None
+                  and self.t_begin <= q[0] <= self.t_end]
+        use = inside if inside else parsed
+        sm = sorted(q[1] for q in use)
+        reasons = sorted({nm for q in use for nm in q[3]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": use[-1][2] if use else None, "reasons": reasons,
+                "samples": len(use), "samples_in_timed_region": len(inside), "samples_total": len(parsed)}
 
     def stop(self):
         if not self.proc:
@@ -106,22 +146,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            p = [c.strip() for c in r.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1]))
-                mx = float(p[2])
-            except ValueError:
-                continue
-            for nm, v in zip(names, p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return self.summarise()
 
 
 def measured_peaks():
@@ -219,11 +244,13 @@ def run_ours(args):
     l0 = an.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark_begin()
     e0.record()
     for i in range(K):
         step(i)
     e1.record()
     barrier()
+    clocks.mark_end()
     ms_total = e0.elapsed_time(e1)
     launches = an.launches - l0
     filt_ms, filt_n = an.profile_read()

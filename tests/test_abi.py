@@ -139,3 +139,25 @@ int main(void) {
         r = subprocess.run([exe], capture_output=True, text=True)
         want = 0 if torch.cuda.is_available() else 13 * 100 + 13
         assert r.returncode == want % 256, r.stdout + r.stderr
+
+
+def test_bench_clock_sampler_parsing():
+    """bench.py's nvidia-smi sampler: rows inside the timed region are told apart by nvidia-smi's own timestamps"""
+    import datetime
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    c = bench.ClockSampler(0)
+    c.rows = ["2026/10/17 01:00:00.000, 0, 120, 1965, 140.2, 0x0000000000000001, Not Active, Not Active, Not Active, Not Active",
+              "2026/10/17 01:00:01.020, 0, 1965, 1965, 640.0, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active",
+              "2026/10/17 01:00:01.040, 0, 1950, 1965, 905.5, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+              "2026/10/17 01:00:01.060, 0, 1965, 1965, 700.0, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active",
+              "garbage", "2026/10/17 01:00:02.000, 0, 120, 1965, 141.0, 0x0000000000000001, Not Active, Not Active, Not Active, Not Active"]
+    c.t_begin = datetime.datetime(2026, 10, 17, 1, 0, 1, 0)
+    c.t_end = datetime.datetime(2026, 10, 17, 1, 0, 1, 100000)
+    out = c.summarise()
+    assert out == {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3,
+                   "samples_in_timed_region": 3, "samples_total": 5}
+    c.t_begin = c.t_end = None          # no marks: every row counts
+    assert c.summarise()["samples"] == 5 and c.summarise()["sm_mhz"] == 1950.0
+    assert bench.ClockSampler.parse_row("x, 0, n/a, 1965, 1, 0, a, b, c, d") is None
