@@ -60,3 +60,20 @@ def test_cpp_mirror_compiles_links_and_fails_loudly_without_gpu(ssb):
             assert r.returncode == 0, r.stdout + r.stderr
         else:
             assert r.returncode == 42, r.stdout + r.stderr   # SSB_ERR_NO_DEVICE: no CPU fallback
+
+
+def test_native_bench_driver_compiles_and_links(ssb):
+    """tools/bench_cabi.cu: the cfg2 step through the C ABI from plain C++/CUDA (no Python, no torch).  Compile + link
+    here; without a device it exits non-zero at its first CUDA call (no CPU fallback anywhere)."""
+    import torch
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "bench_cabi")
+        libdir = os.path.dirname(ssb.library_path())
+        subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-ccbin", "/usr/bin/g++", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "bench_cabi.cu"),
+                               "-o", exe, "-L", libdir, "-lsoundscope_b200", "-Xlinker", "-rpath", "-Xlinker", libdir])
+        r = subprocess.run([exe, "64", "9600", "2", "48000", "loudness", "2", "1"], capture_output=True, text=True)
+        if torch.cuda.is_available():
+            assert r.returncode == 0 and '"driver": "bench_cabi"' in r.stdout, r.stdout + r.stderr
+        else:
+            assert r.returncode != 0
