@@ -125,6 +125,13 @@ int32_t ssb_get_true_peak(ssb_analyzer* h, double* left, double* right);
  * the multi-GPU gather moves.  Asynchronous. */
 size_t ssb_result_stride(const ssb_analyzer* h);
 int32_t ssb_results_device(ssb_analyzer* h, double* d_out);
+/* add_samples followed by the four queries (the per-tick pair analyzer.rs:139-141 + :147-164, tui.rs:1539-1543), as
+ * one call on DEVICE memory: feeds frames_per_stream frames per stream and writes the result rows for the new
+ * position to d_out.  One kernel launch when the batch kernel applies (mono / stereo, whole 320-frame tiles: gating
+ * and the result rows run in the filter kernel's epilogue); otherwise the same as ssb_add_frames_f32_device +
+ * ssb_results_device.  Asynchronous. */
+int32_t ssb_add_frames_f32_device_results(ssb_analyzer* h, const float* d_interleaved, size_t frames_per_stream,
+                                          double* d_out);
 /* Analyzer::calculate_integrated_lufs (analyzer.rs:170-182): a fresh meter at the handle's rate over the whole
  * interleaved file; a `sample_rate*2`-sample chunk that is not whole frames (or an invalid channel count) gives
  * *is_some = 0, the reference's `None`.  The reference builds the meter with Mode::all() but reads nothing except
@@ -254,10 +261,20 @@ int32_t ssb_profile_enable(ssb_analyzer* h, int32_t on);
 int32_t ssb_profile_read(ssb_analyzer* h, double* filter_ms, uint64_t* filter_launches);
 
 /* tests only: pick the filter kernel — 0 automatic, 1 generic (thread per channel), 2 serial many-streams
- * kernel, 3 time-segmented tile kernel, 4 few-streams scan kernel (generic when it does not apply) */
+ * kernel, 3 round-1 time-segmented tile kernel, 4 few-streams scan kernel (generic when it does not apply),
+ * 5 / 6 the warp-pipelined batch kernel with mixed T4/T5 warps / uniform T4 warps */
 int32_t ssb_debug_force_generic(ssb_analyzer* h, int32_t on);
 
+/* The true-peak oversampling factor in use: ebur128's rate rule (4 below 96 kHz, 2 below 192 kHz, 0 above).
+ * ssb_debug_force_true_peak_factor overrides it (2 or 4) — benchmarks only: BASELINE config 5 asks for "4x" at 96 kHz,
+ * where the reference itself oversamples 2x, so results with a forced factor are NOT the reference's. */
+int32_t ssb_true_peak_factor(const ssb_analyzer* h);
+int32_t ssb_debug_force_true_peak_factor(ssb_analyzer* h, int32_t factor);
+
 /* ---- introspection used by the tests ------------------------------------------------------ */
+/* ebur128's find_histogram_index as the gating kernels evaluate it (closed-form guess corrected against the boundary
+ * table), for n block energies in HOST memory: idx_out[i] = bin 0..999, or -1 below the absolute gate (-70 LUFS). */
+int32_t ssb_debug_histogram_index(ssb_analyzer* h, const double* energies, size_t n, int32_t* idx_out);
 int32_t ssb_filter_coeffs(const ssb_analyzer* h, double b[5], double a[5]);
 /* copy the two 1000-bin histograms of stream s to HOST */
 int32_t ssb_histograms(ssb_analyzer* h, size_t stream, uint64_t block[1000], uint64_t shortterm[1000]);

@@ -27,11 +27,31 @@ MODE_LOUDNESS = MODE_I | MODE_LRA | MODE_HISTOGRAM  # M|S|I|LRA|HISTOGRAM, no pe
 OK, ERR_NOMEM, ERR_INVALID_MODE, ERR_INVALID_CHANNEL_INDEX = 0, 1, 2, 3
 
 
+def _host_tag():
+    """What -march=native means on this machine: the CPU flag set (the .so travels between boxes with the tree)."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha1(flags.encode()).hexdigest()[:16]
+
+
 def build(force=False):
-    """Compile liboracle.so with the committed Makefile (gcc only, no reference sources)."""
+    """Compile liboracle.so with the committed Makefile (gcc only, no reference sources).  Built -march=native, so it
+    is rebuilt when the host CPU differs from the one that built the copy in the tree."""
     srcs = [os.path.join(_HERE, f) for f in ("ebur128_ref.c", "spectrum_ref.c", "oracle.h", "Makefile")]
-    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+    stamp = _SO + ".host"
+    tag = _host_tag()
+    try:
+        same_host = open(stamp).read().strip() == tag
+    except OSError:
+        same_host = False
+    if force or not same_host or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+        with open(stamp, "w") as f:
+            f.write(tag)
     return _SO
 
 
@@ -61,6 +81,8 @@ def lib():
         L.orc_histogram_energy.argtypes = [C.c_uint]
         L.orc_histogram_boundary.restype = C.c_double
         L.orc_histogram_boundary.argtypes = [C.c_uint]
+        L.orc_find_histogram_index.restype = C.c_size_t
+        L.orc_find_histogram_index.argtypes = [C.c_double]
         L.orc_calculate_integrated_lufs.argtypes = [C.c_uint32, C.c_uint32, f32p, C.c_size_t, f64p]
         L.orc_batch_new.restype = C.c_void_p
         L.orc_batch_new.argtypes = [C.c_size_t, C.c_uint32, C.c_uint32, C.c_int]
@@ -298,6 +320,11 @@ def histogram_energy(i):
 
 def histogram_boundary(i):
     return lib().orc_histogram_boundary(i)
+
+
+def find_histogram_index(energy):
+    """ebur128 find_histogram_index (the crate's bisection over the 1001 boundaries); energy >= boundary[0]."""
+    return int(lib().orc_find_histogram_index(float(energy)))
 
 
 class Batch:

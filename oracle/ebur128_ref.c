@@ -115,6 +115,9 @@ static size_t find_histogram_index(double energy) {
   return lo;
 }
 
+/* exported for the bin-edge tests (golden set G5): the crate's bisection on the 1001 boundaries */
+size_t orc_find_histogram_index(double energy) { hist_init(); return find_histogram_index(energy); }
+
 static double energy_to_loudness(double e) { return 10.0 * log10(e) - 0.691; }
 
 /* libebur128 ebur128_init_filter: BS.1770 pre-filter (shelf) x RLB high-pass, convolved. */

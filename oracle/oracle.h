@@ -74,6 +74,7 @@ void orc_ebur128_histograms(const orc_ebur128* st, uint64_t block[1000], uint64_
 size_t orc_interp_taps(uint32_t rate, unsigned* factor, unsigned counts[4]);
 double orc_histogram_energy(unsigned i);
 double orc_histogram_boundary(unsigned i);
+size_t orc_find_histogram_index(double energy);   /* ebur128 find_histogram_index (bisection), energy >= boundary[0] */
 
 /* Analyzer::calculate_integrated_lufs — analyzer.rs:170-182.  returns 1 = Some, 0 = None */
 int orc_calculate_integrated_lufs(uint32_t channels, uint32_t sample_rate, const float* samples,

@@ -48,12 +48,12 @@ class SsbError(RuntimeError):
 SYMBOLS = [
     "ssb_abi_version", "ssb_analyzer_create", "ssb_analyzer_destroy", "ssb_create_loudness_meter",
     "ssb_sample_rate", "ssb_channels", "ssb_n_streams", "ssb_last_error", "ssb_set_stream", "ssb_use_own_stream", "ssb_sync",
-    "ssb_launch_count", "ssb_add_frames_f32", "ssb_add_frames_f32_device", "ssb_add_samples", "ssb_reset",
+    "ssb_launch_count", "ssb_add_frames_f32", "ssb_add_frames_f32_device", "ssb_add_frames_f32_device_results", "ssb_add_samples", "ssb_reset",
     "ssb_loudness_momentary", "ssb_loudness_shortterm", "ssb_loudness_global", "ssb_loudness_range",
     "ssb_true_peak", "ssb_sample_peak", "ssb_get_true_peak", "ssb_result_stride", "ssb_results_device",
     "ssb_calculate_integrated_lufs", "ssb_get_fft", "ssb_fft_bins", "ssb_fft_axis", "ssb_fft_batch_device",
     "ssb_process_tick", "ssb_preanalyze_file", "ssb_get_waveform", "ssb_waveform_device", "ssb_mid_side", "ssb_mid_side_device", "ssb_filter_coeffs",
-    "ssb_histograms", "ssb_profile_enable", "ssb_profile_read", "ssb_debug_force_generic",
+    "ssb_histograms", "ssb_profile_enable", "ssb_profile_read", "ssb_debug_force_generic", "ssb_true_peak_factor", "ssb_debug_force_true_peak_factor", "ssb_debug_histogram_index",
     "ssb_pcm_bytes_per_sample", "ssb_pcm_to_f32", "ssb_pcm_to_f32_device", "ssb_add_frames_pcm", "ssb_add_frames_pcm_device",
     "ssb_capture_ring_create", "ssb_capture_ring_destroy", "ssb_capture_ring_capacity", "ssb_capture_ring_written",
     "ssb_capture_ring_push", "ssb_capture_ring_to_vec", "ssb_mic_tick",
@@ -92,6 +92,7 @@ def lib():
         "ssb_launch_count": (C.c_uint64, [vp]),
         "ssb_add_frames_f32": (C.c_int32, [vp, f32p, C.c_size_t]),
         "ssb_add_frames_f32_device": (C.c_int32, [vp, f32p, C.c_size_t]),
+        "ssb_add_frames_f32_device_results": (C.c_int32, [vp, f32p, C.c_size_t, f64p]),
         "ssb_add_samples": (C.c_int32, [vp, f32p, C.c_size_t]),
         "ssb_reset": (C.c_int32, [vp]),
         "ssb_loudness_momentary": (C.c_int32, [vp, f64p]),
@@ -103,6 +104,9 @@ def lib():
         "ssb_get_true_peak": (C.c_int32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "ssb_result_stride": (C.c_size_t, [vp]),
         "ssb_results_device": (C.c_int32, [vp, f64p]),
+        "ssb_debug_histogram_index": (C.c_int32, [vp, f64p, C.c_size_t, vp]),
+        "ssb_true_peak_factor": (C.c_int32, [vp]),
+        "ssb_debug_force_true_peak_factor": (C.c_int32, [vp, C.c_int32]),
         "ssb_calculate_integrated_lufs": (C.c_int32, [vp, C.c_uint32, f32p, C.c_size_t, C.POINTER(C.c_double), i32p]),
         "ssb_get_fft": (C.c_int32, [vp, f32p, C.c_size_t, f64p, C.c_size_t, szp]),
         "ssb_fft_bins": (C.c_int32, [C.c_size_t, C.c_uint32, szp, szp]),

@@ -42,8 +42,16 @@ class BatchAnalyzer:
         check(self._h, lib().ssb_debug_force_generic(self._h, 1 if on else 0))
 
     def force_kernel(self, which):
-        """tests: 0 automatic, 1 generic, 2 serial many-streams kernel, 3 time-segmented tile kernel"""
+        """tests: 0 automatic, 1 generic, 2 serial many-streams kernel, 3 round-1 tile kernel, 4 scan kernel,
+        5 / 6 warp-pipelined batch kernel (mixed T4/T5 warps / uniform T4 warps)"""
         check(self._h, lib().ssb_debug_force_generic(self._h, int(which)))
+
+    def true_peak_factor(self):
+        return lib().ssb_true_peak_factor(self._h)
+
+    def force_true_peak_factor(self, factor):
+        """benchmarks only: 2 or 4 regardless of ebur128's rate rule (results are then NOT the reference's)"""
+        check(self._h, lib().ssb_debug_force_true_peak_factor(self._h, int(factor)))
 
     def profile(self, on=True):
         check(self._h, lib().ssb_profile_enable(self._h, 1 if on else 0))
@@ -65,6 +73,18 @@ class BatchAnalyzer:
         assert x.is_cuda and x.is_contiguous() and x.dtype.is_floating_point and x.element_size() == 4
         assert x.shape[0] == self.n_streams and x.shape[2] == self.channels
         check(self._h, lib().ssb_add_frames_f32_device(self._h, C.c_void_p(x.data_ptr()), x.shape[1]))
+
+    def add_frames_results_device(self, x, out=None):
+        """add_frames_device + results_device as one C-ABI call (one kernel launch when the batch kernel applies).
+        Returns the [n_streams, 4+2C] f64 CUDA tensor of result rows for the position after the feed."""
+        import torch
+        assert x.is_cuda and x.is_contiguous() and x.dtype.is_floating_point and x.element_size() == 4
+        assert x.shape[0] == self.n_streams and x.shape[2] == self.channels
+        if out is None:
+            out = torch.empty((self.n_streams, self.stride), dtype=torch.float64, device=x.device)
+        check(self._h, lib().ssb_add_frames_f32_device_results(self._h, C.c_void_p(x.data_ptr()), x.shape[1],
+                                                               C.c_void_p(out.data_ptr())))
+        return out
 
     def add_frames_host(self, x):
         """x: host float32 array / pinned tensor [n_streams, frames, channels]; H2D copy is inside the call."""
@@ -143,6 +163,13 @@ class BatchAnalyzer:
 
     def sample_peak(self):
         return self._col(lib().ssb_sample_peak, self.channels)
+
+    def histogram_index(self, energies):
+        """find_histogram_index as the gating kernels evaluate it: bin per block energy, -1 below the absolute gate."""
+        e = np.ascontiguousarray(energies, dtype=np.float64)
+        out = np.empty(e.size, dtype=np.int32)
+        check(self._h, lib().ssb_debug_histogram_index(self._h, e.ctypes.data, e.size, out.ctypes.data))
+        return out
 
     def histograms(self, stream):
         blk, st = np.zeros(1000, dtype=np.uint64), np.zeros(1000, dtype=np.uint64)

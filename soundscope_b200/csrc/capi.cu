@@ -45,6 +45,7 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
   kweight_coeffs(rate, lp.b, lp.a);
   for (int i = 0; i < 5; i++) lp.na[i] = -lp.a[i];
   tile_handoff_matrix(lp.a, lp.handoff);
+  tile_handoff_power(lp.a, 80, lp.handoff80);
   if (channels <= 2 && h->n_streams <= 64) {
     std::vector<double> tab(scan_power_table_doubles());
     scan_power_table(lp.a, tab.data());
@@ -96,6 +97,7 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
   h->gated_upto = 0;
   h->ring_pos = 0;
   h->results_valid = false;
+  h->dres_valid = false;
   CK(launch_reset(st, (int)channels, h->stream, &h->launches));
   h->meter_ok = true;
   return SSB_OK;
@@ -150,11 +152,15 @@ static int32_t flush_gating(ssb_analyzer* h) {
 }
 
 // feed `frames` frames per stream from device memory laid out [stream][in_stride_frames][C]
-int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in_stride_frames) {
+int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in_stride_frames, double* d_results,
+                    bool* written) {
+  if (written) *written = false;
   if (!h->meter_ok) return fail(h, SSB_ERR_NOMEM, "the loudness meter is not initialised (a previous create/reinit failed)");
   const uint32_t s100 = h->lp.s100;
   const size_t C = h->channels;
   size_t done = 0;
+  h->results_valid = false;
+  h->dres_valid = false;
   while (done < frames) {
     const uint32_t pos = (uint32_t)(h->total_frames % s100);
     const uint64_t bucket0 = h->total_frames / s100;
@@ -179,13 +185,37 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
       CK(cudaEventRecord(ev0, h->stream));
     }
     size_t tiled = 0;
-    if (h->d_scan_powers && (h->force_kernel == 0 || h->force_kernel == 4) && scan_path_usable(h->lp, h->st, n)) {
+    const int fk = h->force_kernel;
+    const bool last_chunk = done + n == frames;
+    // the second-generation batch kernel: mono / stereo, below the stream count where the serial kernel takes over
+    const int wvariant = fk == 6 ? 1 : 0;
+    const bool want_wtile = (fk == 5 || fk == 6 || (fk == 0 && h->st.n_streams < serial_min_streams()));
+    if (h->d_scan_powers && (fk == 0 || fk == 4) && scan_path_usable(h->lp, h->st, n)) {
       CK(launch_loudness_scan(h->lp, h->st, h->d_scan_powers, d_in + done * C, n, in_stride_frames, pos, bucket0,
                               h->ring_pos, h->stream, &h->launches));
       tiled = n;
-    } else if (h->force_kernel != 1 && h->force_kernel != 4 && tile_path_usable(h->lp, h->st, d_in + done * C, n, in_stride_frames))
+    } else if (want_wtile && wtile_path_usable(h->lp, h->st, d_in + done * C, n, in_stride_frames, wvariant)) {
+      // results fused into the filter launch when the caller wants them and this launch ends the feed on whole tiles
+      ResultsArgs ra{};
+      const ResultsArgs* rap = nullptr;
+      const uint64_t frames_after = h->total_frames + n;
+      const uint64_t done_after = frames_after / s100;
+      if (d_results && last_chunk) {
+        const bool pending = done_after > h->gated_upto;
+        ra = make_results_args(h->st, done_after, (frames_after % s100) == 0, h->ring_pos, h->mode, d_results,
+                               pending ? h->gated_upto : 1, pending ? done_after - 1 : 0, nullptr);
+        rap = &ra;
+      }
+      bool wrote = false;
+      CK(launch_loudness_wtile(h->lp, h->st, h->gp, d_in + done * C, n, in_stride_frames, pos, bucket0, wvariant, rap,
+                               h->sm_count, h->device, h->stream, &h->launches, &tiled, &wrote));
+      if (wrote) {
+        if (done_after > h->gated_upto) h->gated_upto = done_after;
+        if (written) *written = true;
+      }
+    } else if (fk != 1 && fk != 4 && fk != 5 && fk != 6 && tile_path_usable(h->lp, h->st, d_in + done * C, n, in_stride_frames))
       CK(launch_loudness_tile(h->lp, h->st, d_in + done * C, n, in_stride_frames, pos, bucket0, h->stream,
-                              &h->launches, &tiled, h->force_kernel));
+                              &h->launches, &tiled, fk, h->sm_count));
     if (tiled < n) {
       const uint64_t t2 = h->total_frames + tiled;
       CK(launch_loudness_generic(h->lp, h->st, d_in + (done + tiled) * C, n - tiled, in_stride_frames,
@@ -196,7 +226,6 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
     if (h->st.ring_frames) h->ring_pos = (h->ring_pos + n) % h->st.ring_frames;
     done += n;
   }
-  h->results_valid = false;
   return SSB_OK;
 }
 
@@ -223,8 +252,11 @@ const std::pair<std::vector<double>, std::vector<double>>& fft_axis_cached(ssb_a
 static int32_t refresh_results(ssb_analyzer* h) {
   if (!h->meter_ok) return fail(h, SSB_ERR_NOMEM, "the loudness meter is not initialised (a previous create/reinit failed)");
   if (h->results_valid) return SSB_OK;
-  const int32_t rrc = launch_results_now(h);
-  if (rrc) return rrc;
+  if (!h->dres_valid) {
+    const int32_t rrc = launch_results_now(h);
+    if (rrc) return rrc;
+    h->dres_valid = true;
+  }
   const size_t stride = 4 + 2 * (size_t)h->channels;
   CK(cudaMemcpyAsync(h->h_results, h->d_results, h->n_streams * stride * sizeof(double), cudaMemcpyDeviceToHost,
                      h->stream));
@@ -331,6 +363,7 @@ int32_t ssb_analyzer_create(ssb_analyzer** out, uint32_t channels, uint32_t rate
   ssb_analyzer* h = new (std::nothrow) ssb_analyzer();
   if (!h) return SSB_ERR_NOMEM;
   h->device = device;
+  h->sm_count = prop.multiProcessorCount;
   h->mode = mode;
   h->n_streams = n_streams;
   h->flags = flags;
@@ -436,6 +469,19 @@ int32_t ssb_add_frames_f32_device(ssb_analyzer* h, const float* d_interleaved, s
   return feed_device(h, d_interleaved, frames_per_stream, frames_per_stream);
 }
 
+int32_t ssb_add_frames_f32_device_results(ssb_analyzer* h, const float* d_interleaved, size_t frames_per_stream,
+                                          double* d_out) {
+  if (!h || !d_out) return SSB_ERR_INVALID_ARG;
+  if (frames_per_stream && !d_interleaved) return fail(h, SSB_ERR_INVALID_ARG, "null input");
+  DeviceGuard g(h->device);
+  bool wrote = false;
+  if (frames_per_stream) {
+    const int32_t rc = feed_device(h, d_interleaved, frames_per_stream, frames_per_stream, d_out, &wrote);
+    if (rc) return rc;
+  }
+  return wrote ? SSB_OK : ssb_results_device(h, d_out);
+}
+
 int32_t ssb_add_frames_f32(ssb_analyzer* h, const float* interleaved, size_t frames_per_stream) {
   if (!h) return SSB_ERR_INVALID_ARG;
   if (frames_per_stream == 0) return SSB_OK;
@@ -450,8 +496,14 @@ int32_t ssb_add_frames_f32(ssb_analyzer* h, const float* interleaved, size_t fra
   CK(cudaEventSynchronize(h->ev_consumed[i]));
   CK(cudaMemcpyAsync(h->d_stage[i], interleaved, floats * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   CK(cudaEventRecord(h->ev_copied[i], h->stream));
-  rc = feed_device(h, h->d_stage[i], frames_per_stream, frames_per_stream);
-  if (rc) return rc;
+  {
+    // the rows land in the handle's own result buffer when the filter launch can write them itself, so the query that
+    // usually follows (get_shortterm_lufs after add_samples, tui.rs:1539-1543) is a copy, not a launch
+    bool wrote = false;
+    rc = feed_device(h, h->d_stage[i], frames_per_stream, frames_per_stream, h->d_results, &wrote);
+    if (rc) return rc;
+    h->dres_valid = wrote;
+  }
   CK(cudaEventRecord(h->ev_consumed[i], h->stream));
   CK(cudaEventSynchronize(h->ev_copied[i]));  // caller may reuse its buffer; kernels keep running
   return SSB_OK;
@@ -474,6 +526,7 @@ int32_t ssb_reset(ssb_analyzer* h) {
   h->gated_upto = 0;
   h->ring_pos = 0;
   h->results_valid = false;
+  h->dres_valid = false;
   return SSB_OK;
 }
 
@@ -631,7 +684,7 @@ static int32_t one_shot_integrated(ssb_analyzer* h, uint32_t channels, const flo
       double* d_fb = reinterpret_cast<double*>(reinterpret_cast<char*>(tmp->d_scratch) + own_in);
       // 1 s chunks (+0.4 s run-in) until the file outgrows four chunks per SM, then longer ones
       size_t chunk_buckets = 10;
-      const size_t max_chunks = 4 * 148;
+      const size_t max_chunks = 4 * (size_t)(tmp->sm_count > 0 ? tmp->sm_count : 148);
       if ((n_buckets + chunk_buckets - 1) / chunk_buckets > max_chunks) chunk_buckets = (n_buckets + max_chunks - 1) / max_chunks;
       e = launch_loudness_scan_file(tmp->lp, tmp->st, tmp->d_scan_powers, d, frames, d_fb, stride, chunk_buckets,
                                     tmp->stream, &tmp->launches);
@@ -908,6 +961,17 @@ int32_t ssb_debug_force_generic(ssb_analyzer* h, int32_t on) {
   return SSB_OK;
 }
 
+int32_t ssb_true_peak_factor(const ssb_analyzer* h) { return h ? h->lp.tp_factor : 0; }
+
+int32_t ssb_debug_force_true_peak_factor(ssb_analyzer* h, int32_t factor) {
+  if (!h || (factor != 2 && factor != 4)) return SSB_ERR_INVALID_ARG;
+  if (!h->lp.do_true_peak) return fail(h, SSB_ERR_INVALID_MODE, "mode lacks TRUE_PEAK (Error::InvalidMode)");
+  DeviceGuard g(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  h->lp.tp_factor = truepeak_taps(h->rate, h->lp.tp4, h->lp.tp2, factor);
+  return SSB_OK;
+}
+
 int32_t ssb_profile_enable(ssb_analyzer* h, int32_t on) {
   if (!h) return SSB_ERR_INVALID_ARG;
   DeviceGuard g(h->device);
@@ -937,6 +1001,23 @@ int32_t ssb_filter_coeffs(const ssb_analyzer* h, double b[5], double a[5]) {
   if (!h || !b || !a) return SSB_ERR_INVALID_ARG;
   memcpy(b, h->lp.b, sizeof(h->lp.b));
   memcpy(a, h->lp.a, sizeof(h->lp.a));
+  return SSB_OK;
+}
+
+int32_t ssb_debug_histogram_index(ssb_analyzer* h, const double* energies, size_t n, int32_t* idx_out) {
+  if (!h || (n && (!energies || !idx_out))) return SSB_ERR_INVALID_ARG;
+  if (!h->meter_ok) return fail(h, SSB_ERR_NOMEM, "the loudness meter is not initialised");
+  if (!n) return SSB_OK;
+  DeviceGuard g(h->device);
+  const size_t in_bytes = (n * sizeof(double) + 255) & ~(size_t)255;
+  int32_t rc = ensure_scratch_device(h, in_bytes + n * sizeof(int32_t));
+  if (rc) return rc;
+  double* d_e = reinterpret_cast<double*>(h->d_scratch);
+  int32_t* d_out = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(h->d_scratch) + in_bytes);
+  CK(cudaMemcpyAsync(d_e, energies, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(launch_histogram_index(h->st, d_e, n, d_out, h->stream));
+  CK(cudaMemcpyAsync(idx_out, d_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return SSB_OK;
 }
 

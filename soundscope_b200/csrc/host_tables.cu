@@ -57,9 +57,10 @@ void default_channel_weights(uint32_t channels, float w[kMaxChannels], uint64_t*
   *active_mask = mask;
 }
 
-int truepeak_taps(uint32_t rate, float tp4[3][12], float tp2[24]) {
+int truepeak_taps(uint32_t rate, float tp4[3][12], float tp2[24], int force_factor) {
   const int taps = 49;
-  const int factor = rate < 96000 ? 4 : (rate < 192000 ? 2 : 0);
+  // ebur128's rate rule; force_factor (2 or 4) overrides it for the explicitly non-parity benchmark variant
+  const int factor = force_factor ? force_factor : (rate < 96000 ? 4 : (rate < 192000 ? 2 : 0));
   memset(tp4, 0, sizeof(float) * 36);
   memset(tp2, 0, sizeof(float) * 24);
   if (!factor) return 0;

@@ -11,7 +11,7 @@
 // State layout in HBM (all stream-major):
 //   filt[n][C][4] f64 | bucket[n][C][64] f64 | block_hist[n][1000] u32 | st_hist[n][1000] u32
 //   speak/tpeak[n][C] f32 | tphist[n][C][24] f32 | ring[n][ring_frames][C] f64 (optional)
-#include "ssb_internal.cuh"
+#include "loudness_results.cuh"
 
 namespace ssb {
 
@@ -135,41 +135,6 @@ cudaError_t launch_loudness_generic(const LoudParams& p, const LoudState& st, co
 // ------------------------------------------------------------------------------------------------
 // gating: block / short-term energies of the buckets completed by the last filter launch
 // ------------------------------------------------------------------------------------------------
-// ebur128 find_histogram_index: the bin i with boundaries[i] <= energy < boundaries[i+1] (clamped to 0..999).
-// The crate bisects the 1001 boundaries; the same index is reached here from a closed-form guess
-// (bins are 0.1 LU wide from -70 LUFS) corrected against the table, which replaces ten dependent loads by two.
-__device__ __forceinline__ int find_histogram_index(const double* __restrict__ bounds, double energy) {
-  int idx = (int)floor((10.0 * log10(energy) - 0.691 + 70.0) * 10.0);
-  idx = idx < 0 ? 0 : (idx > 999 ? 999 : idx);
-  while (idx > 0 && energy < bounds[idx]) --idx;
-  while (idx < 999 && energy >= bounds[idx + 1]) ++idx;
-  return idx;
-}
-
-// channel-weighted sum of NB buckets ending at bucket j (ebur128 calc_gating_block: per channel sum oldest to
-// newest, surround channels x1.41, summed over channels in channel order).  All NB loads are issued before the
-// first add: one memory latency per channel instead of NB.
-template <int NB>
-__device__ __forceinline__ double window_energy_t(const double* __restrict__ bk, const GateParams& g, uint64_t j) {
-  double sum = 0.0;
-  for (int c = 0; c < g.channels; c++) {
-    const float w = g.weight[c];
-    if (w == 0.0f) continue;
-    double v[NB];
-#pragma unroll
-    for (int k = 0; k < NB; k++) v[k] = __ldcg(&bk[c * kNB + (int)((j - (uint64_t)(NB - 1 - k)) % kNB)]);
-    double ch = 0.0;
-#pragma unroll
-    for (int k = 0; k < NB; k++) ch += v[k];
-    if (w != 1.0f) ch *= 1.41;
-    sum += ch;
-  }
-  return sum / (double)((uint64_t)NB * g.s100);
-}
-__device__ __forceinline__ double window_energy(const double* __restrict__ bk, const GateParams& g, uint64_t j, int nb) {
-  return nb == 4 ? window_energy_t<4>(bk, g, j) : window_energy_t<30>(bk, g, j);
-}
-
 __global__ void __launch_bounds__(128)
 k_gating(const GateParams g, size_t n_streams, const double* __restrict__ bucket,
          uint32_t* __restrict__ block_hist, uint32_t* __restrict__ st_hist,
@@ -245,41 +210,6 @@ cudaError_t launch_file_gating(const GateParams& g, const LoudState& st, const d
 // ------------------------------------------------------------------------------------------------
 // results: one warp per stream
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-__device__ __forceinline__ double energy_to_loudness(double e) { return 10.0 * log10(e) - 0.691; }
-
-// mean square of the last `win_frames` frames of the ring ending at ring_pos (ebur128 calc_gating_block
-// over the ring; the ring starts zeroed, so an under-filled window reads zeros exactly as the crate does)
-__device__ double ring_energy(const double* __restrict__ rg, const GateParams& g, size_t ring_frames,
-                              size_t ring_pos, size_t win_frames, int lane) {
-  double sum = 0.0;
-  for (int c = 0; c < g.channels; c++) {
-    const float w = g.weight[c];
-    if (w == 0.0f) continue;
-    double part = 0.0;
-    for (size_t i = lane; i < win_frames; i += 32) {
-      size_t idx = ring_pos + ring_frames - win_frames + i;
-      if (idx >= ring_frames) idx -= ring_frames;
-      const double y = rg[idx * g.channels + c];
-      part = fma(y, y, part);
-    }
-    double ch = warp_sum(part);
-    if (w != 1.0f) ch *= 1.41;
-    sum += ch;
-  }
-  return sum / (double)win_frames;
-}
-
 // Momentary / short-term energies from the ring of K-weighted samples (SSB_FLAG_RING handles: few streams,
 // so one 512-thread block per stream; fixed-order tree reduction).  Window sums follow ebur128
 // calc_gating_block: per channel sum of y^2 over the last W frames ending at ring_pos, surround x1.41.
@@ -317,186 +247,12 @@ k_ring_energy(const GateParams g, const double* __restrict__ ring, size_t ring_f
   }
 }
 
-__global__ void __launch_bounds__(128)
-k_results(const GateParams g, size_t n_streams, const double* __restrict__ bucket,
-          const uint32_t* __restrict__ block_hist, const uint32_t* __restrict__ st_hist,
-          const float* __restrict__ speak, const float* __restrict__ tpeak, const double* __restrict__ ring,
-          size_t ring_frames, size_t ring_pos, const double* __restrict__ energies,
-          const double* __restrict__ bounds, uint64_t buckets_done, int aligned, int mode,
-          double* __restrict__ out, uint32_t* __restrict__ block_hist_rw, uint32_t* __restrict__ st_hist_rw,
-          uint64_t gate_first, uint64_t gate_last, const double* __restrict__ ring_e) {
+__global__ void __launch_bounds__(128, 4)
+k_results(const __grid_constant__ GateParams g, const __grid_constant__ ResultsArgs ra, size_t n_streams) {
   const size_t s = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (s >= n_streams) return;
-  // buckets completed since the last gating pass are gated here first (one lane per bucket), so a step that
-  // ends in a query costs one launch less; the histogram reads below then go to L2 (__ldcg)
-  if (gate_last >= gate_first) {
-    const double* bkp = bucket + s * (size_t)g.channels * kNB;
-    for (uint64_t j = gate_first + lane; j <= gate_last; j += 32) {
-      if (g.do_i && j >= 3) {
-        const double e = window_energy(bkp, g, j, 4);
-        if (e >= bounds[0]) atomicAdd(&block_hist_rw[s * kHistBins + find_histogram_index(bounds, e)], 1u);
-      }
-      if (g.do_lra && j >= 29 && (j - 29) % 10 == 0) {
-        const double e = window_energy(bkp, g, j, 30);
-        if (e >= bounds[0]) atomicAdd(&st_hist_rw[s * kHistBins + find_histogram_index(bounds, e)], 1u);
-      }
-    }
-    __threadfence();
-    __syncwarp();
-  }
-  const int C = g.channels;
-  const size_t stride = 4 + 2 * (size_t)C;
-  double* o = out + s * stride;
-  const double NaN = __longlong_as_double(0x7ff8000000000000ll);
-  const double NEG_INF = __longlong_as_double(0xfff0000000000000ll);
-
-  // --- momentary / short-term ---
-  double e_m = NaN, e_s = NaN;
-  if (ring_e) {
-    e_m = ring_e[s * 2];
-    if ((mode & SSB_MODE_S) == SSB_MODE_S) e_s = ring_e[s * 2 + 1];
-  } else if (ring) {
-    const double* rg = ring + s * ring_frames * C;
-    e_m = ring_energy(rg, g, ring_frames, ring_pos, (size_t)g.s100 * 4, lane);
-    if ((mode & SSB_MODE_S) == SSB_MODE_S) e_s = ring_energy(rg, g, ring_frames, ring_pos, (size_t)g.s100 * 30, lane);
-  } else if (aligned) {
-    // buckets not yet produced since the last reset hold zeros, like the crate's zeroed ring
-    const double* bk = bucket + s * (size_t)C * kNB;
-    const uint64_t j = buckets_done + kNB - 1;  // last completed bucket, biased to stay non-negative mod kNB
-    e_m = window_energy(bk, g, j, 4);
-    if ((mode & SSB_MODE_S) == SSB_MODE_S) e_s = window_energy(bk, g, j, 30);
-  }
-  if (lane == 0) {
-    o[0] = (e_m == e_m) ? (e_m <= 0.0 ? NEG_INF : energy_to_loudness(e_m)) : NaN;
-    o[1] = (e_s == e_s) ? (e_s <= 0.0 ? NEG_INF : energy_to_loudness(e_s)) : NaN;
-  }
-
-  // Each histogram is read once into registers, lane-major: lane l owns bins [32 l, 32 l + 32) (eight 16-byte
-  // loads from L2), so sums are per-lane loops plus one warp reduction and the LRA percentile walk is a warp
-  // scan over lane totals plus a 32-step walk in one lane's registers — no dependent global loads.
-  const int bin0 = lane * 32;
-  // --- integrated: ebur128 gated_loudness, histogram branch ---
-  double integrated = NaN;
-  if ((mode & SSB_MODE_I) == SSB_MODE_I) {
-    const uint4* hb4 = reinterpret_cast<const uint4*>(block_hist + s * kHistBins) + lane * 8;
-    uint32_t hreg[32];
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (bin0 + 4 * q < kHistBins) v = __ldcg(hb4 + q);   // 1000 = 31 * 32 + 8: whole quads only
-      hreg[4 * q] = v.x; hreg[4 * q + 1] = v.y; hreg[4 * q + 2] = v.z; hreg[4 * q + 3] = v.w;
-    }
-    double pw = 0.0;
-    unsigned long long cnt = 0;
-#pragma unroll
-    for (int t = 0; t < 32; t++) {
-      if (hreg[t]) pw = fma((double)hreg[t], energies[bin0 + t], pw);
-      cnt += hreg[t];
-    }
-    pw = warp_sum(pw);
-    cnt = warp_sum_u64(cnt);
-    if (!cnt) integrated = NEG_INF;
-    else {
-      double rel = pw / (double)cnt;
-      rel *= 0.1;  // 10^(-10/10)
-      int start;
-      if (rel < bounds[0]) start = 0;
-      else {
-        start = find_histogram_index(bounds, rel);
-        if (rel > energies[start]) ++start;
-      }
-      double gp = 0.0;
-      unsigned long long gc = 0;
-#pragma unroll
-      for (int t = 0; t < 32; t++) {
-        if (hreg[t] && bin0 + t >= start) {
-          gp = fma((double)hreg[t], energies[bin0 + t], gp);
-          gc += hreg[t];
-        }
-      }
-      gp = warp_sum(gp);
-      gc = warp_sum_u64(gc);
-      integrated = gc ? energy_to_loudness(gp / (double)gc) : NEG_INF;
-    }
-  }
-  // --- loudness range: ebur128 loudness_range, histogram branch (EBU Tech 3342) ---
-  double lra = NaN;
-  if ((mode & SSB_MODE_LRA) == SSB_MODE_LRA) {
-    const uint4* hs4 = reinterpret_cast<const uint4*>(st_hist + s * kHistBins) + lane * 8;
-    uint32_t hreg[32];
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (bin0 + 4 * q < kHistBins) v = __ldcg(hs4 + q);
-      hreg[4 * q] = v.x; hreg[4 * q + 1] = v.y; hreg[4 * q + 2] = v.z; hreg[4 * q + 3] = v.w;
-    }
-    double pw = 0.0;
-    unsigned long long cnt = 0;
-#pragma unroll
-    for (int t = 0; t < 32; t++) {
-      if (hreg[t]) pw = fma((double)hreg[t], energies[bin0 + t], pw);
-      cnt += hreg[t];
-    }
-    pw = warp_sum(pw);
-    cnt = warp_sum_u64(cnt);
-    if (!cnt) lra = 0.0;
-    else {
-      const double stl_integrated = 0.01 * (pw / (double)cnt);  // 10^(-20/10)
-      int index;
-      if (stl_integrated < bounds[0]) index = 0;
-      else {
-        index = find_histogram_index(bounds, stl_integrated);
-        if (stl_integrated > energies[index]) ++index;
-      }
-      // lane totals above the relative gate, their exclusive prefix, and the grand total
-      unsigned long long mine = 0;
-#pragma unroll
-      for (int t = 0; t < 32; t++) if (bin0 + t >= index) mine += hreg[t];
-      unsigned long long incl = mine;
-#pragma unroll
-      for (int o2 = 1; o2 < 32; o2 <<= 1) {
-        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o2);
-        if (lane >= o2) incl += up;
-      }
-      const unsigned long long above = __shfl_sync(0xffffffffu, incl, 31);
-      if (!above) lra = 0.0;
-      else {
-        const unsigned long long excl = incl - mine;
-        const unsigned long long lo = (unsigned long long)((double)(above - 1) * 0.1 + 0.5);
-        const unsigned long long hi = (unsigned long long)((double)(above - 1) * 0.95 + 0.5);
-        // ebur128 walks `while (size <= p) size += hist[j++]` and takes bin j-1: the first bin whose running
-        // count exceeds p.  The lane whose range (excl, incl] contains p+1 finds it in its registers.
-        int lo_bin = -1, hi_bin = -1;
-        unsigned long long run = excl;
-#pragma unroll
-        for (int t = 0; t < 32; t++) {
-          if (bin0 + t >= index) {
-            run += hreg[t];
-            if (lo_bin < 0 && run > lo && excl <= lo) lo_bin = bin0 + t;
-            if (hi_bin < 0 && run > hi && excl <= hi) hi_bin = bin0 + t;
-          }
-        }
-        // exactly one lane found each (its excl <= p < incl); max-reduce the -1s away
-#pragma unroll
-        for (int o2 = 16; o2 > 0; o2 >>= 1) {
-          lo_bin = max(lo_bin, __shfl_xor_sync(0xffffffffu, lo_bin, o2));
-          hi_bin = max(hi_bin, __shfl_xor_sync(0xffffffffu, hi_bin, o2));
-        }
-        lra = energy_to_loudness(energies[hi_bin]) - energy_to_loudness(energies[lo_bin]);
-      }
-    }
-  }
-  if (lane == 0) {
-    o[2] = integrated;
-    o[3] = lra;
-  }
-  // --- peaks: EbuR128::true_peak = max(true_peak, sample_peak) ---
-  for (int c = lane; c < C; c += 32) {
-    const float spv = speak[s * C + c], tpv = tpeak[s * C + c];
-    o[4 + c] = (double)fmaxf(spv, tpv);
-    o[4 + C + c] = (double)spv;
-  }
+  results_for_stream(g, ra, s, lane);
 }
 
 cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
@@ -512,11 +268,21 @@ cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t bu
   }
   const int tpb = 128;
   const size_t threads = st.n_streams * 32;
-  k_results<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, s>>>(
-      g, st.n_streams, st.bucket, st.block_hist, st.st_hist, st.speak, st.tpeak, st.ring, st.ring_frames,
-      ring_pos, st.hist_energies, st.hist_boundaries, buckets_done, aligned, mode, d_out, st.block_hist, st.st_hist,
-      gate_first, gate_last, ring_e);
+  const ResultsArgs ra = make_results_args(st, buckets_done, aligned, ring_pos, mode, d_out, gate_first, gate_last, ring_e);
+  k_results<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, s>>>(g, ra, st.n_streams);
   if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// find_histogram_index on an array of energies (tests: bin-edge cases against the crate's bisection); -1 below the
+// absolute gate, as the `e >= boundaries[0]` tests of the gating code
+__global__ void k_histogram_index(const double* __restrict__ e, size_t n, const double* __restrict__ bounds, int32_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = e[i] >= bounds[0] ? find_histogram_index(bounds, e[i]) : -1;
+}
+cudaError_t launch_histogram_index(const LoudState& st, const double* d_e, size_t n, int32_t* d_out, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  k_histogram_index<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_e, n, st.hist_boundaries, d_out);
   return cudaGetLastError();
 }
 

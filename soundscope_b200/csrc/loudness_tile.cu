@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include "ssb_internal.cuh"
+#include "tma_ptx.cuh"
 
 namespace ssb {
 
@@ -51,52 +52,6 @@ struct TileArgs {
   int do_sample_peak;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ unsigned mbar_try(uint64_t* bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok;
-}
-// bounded spin: a broken pipeline traps instead of hanging the device
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  unsigned spins = 0;
-  while (!mbar_try(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
-  }
-}
-// the same wait for a fully active warp: the exit test is a vote, so the branch is warp-uniform and the code
-// after it stays eligible for the uniform datapath (coefficients in uniform registers instead of a third
-// register operand on every recursion DFMA)
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, unsigned parity) {
-  unsigned spins = 0;
-  while (!__all_sync(0xffffffffu, mbar_try(bar, parity))) {
-    if (++spins > (1u << 26)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 __device__ __forceinline__ void bar_sync_compute(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 
 // d = D v with D = [[1,0,0,0],[1,-1,0,0],[1,-2,1,0],[1,-3,3,-1]] (finite differences; D is its own inverse).
@@ -825,23 +780,8 @@ k_loudness_rows_any(const __grid_constant__ CUtensorMap tmap, const __grid_const
 #undef SSB_FILTER_STEP
 #undef SSB_TP_STEP
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
+using EncodeTiledFn = TmaEncodeTiledFn;
+EncodeTiledFn encode_fn() { return tma_encode_fn(); }
 
 // ---- host: D * A^n * D in double-double arithmetic, rounded once to double ----------------------
 struct dd { double hi, lo; };
@@ -968,18 +908,29 @@ cudaError_t launch_any_cfg(const CUtensorMap& tmap, const TileArgs& args, unsign
 
 }  // namespace
 
+TmaEncodeTiledFn tma_encode_fn() {
+  static TmaEncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<TmaEncodeTiledFn>(p);
+    return (TmaEncodeTiledFn) nullptr;
+  }();
+  return fn;
+}
+
 constexpr int kTileT = 4;
 constexpr int kTileFMax = 256;
 
-// stream count from which the serial many-streams kernel replaces the time-segmented one
-// (SSB_SERIAL_MIN overrides it; the tests use that to run both kernels on small batches)
-static size_t serial_min_streams() {
-  static size_t v = 0;
-  if (!v) {
+// stream count from which the serial many-streams kernel replaces the time-segmented ones
+// (SSB_SERIAL_MIN overrides it; the tests use that to run both kernels on small batches); read once, thread-safe
+size_t serial_min_streams() {
+  static const size_t v = [] {
     const char* e = getenv("SSB_SERIAL_MIN");
-    v = e ? (size_t)strtoull(e, nullptr, 10) : 16384;
-    if (!v) v = 1;
-  }
+    size_t x = e ? (size_t)strtoull(e, nullptr, 10) : 16384;
+    return x ? x : (size_t)1;
+  }();
   return v;
 }
 
@@ -1001,20 +952,14 @@ bool tile_path_usable(const LoudParams& p, const LoudState& st, const float* d_i
 // Filters the first floor(frames / F) * F frames; returns how many frames were consumed in *consumed.
 cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
                                  size_t in_stride_frames, uint32_t pos0, uint64_t bucket0, cudaStream_t s,
-                                 uint64_t* launches, size_t* consumed, int force_kernel) {
+                                 uint64_t* launches, size_t* consumed, int force_kernel, int sm_count) {
   *consumed = 0;
   const int C = p.channels;
   // force_kernel: 0 = choose by stream count, 2 = serial rows kernel, 3 = time-segmented kernel (tests)
   const bool any_c = C > 2;
   const bool serial = any_c || force_kernel == 2 || (force_kernel != 3 && st.n_streams >= serial_min_streams());
   const int tile_f = any_c ? kAnyF : (serial ? kSerialF : kTileFMax);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = sm_count > 0 ? sm_count : 148;   // of the handle's device (queried at create)
   const bool any_tp = p.do_true_peak && p.tp_factor;
   // multichannel kernel: a box holds whole warps' worth of streams, rounded down to the swizzle period of 8 rows
   int box_rows = any_c ? (any_tp ? kAnyWarpsTp : kAnyWarps) * (32 / C) / 8 * 8 : (serial ? kRowsSerial : kRows);

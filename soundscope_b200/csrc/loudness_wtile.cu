@@ -1,0 +1,634 @@
+// loudness_wtile.cu — the batch K-weighting + gated-RMS (+ peaks) kernel for a few thousand streams per GPU
+// (BASELINE config 2), second generation: warp-private TMA pipelines, balanced sub-partitions, fused results.
+//
+// Same arithmetic as the reference's `add_samples` (src/analyzer.rs:139-141 -> ebur128 add_frames_f32: 4th-order
+// DF-II K-weighting in f64, y^2 summed per 100 ms, sample peak, polyphase true peak) followed, optionally in the
+// same launch, by the queries of src/analyzer.rs:147-164 (loudness_results.cuh).
+//
+// What bounds it: the FP64 pipe (16 lanes per SM sub-partition: a warp DFMA holds it for 2 cycles), not HBM — a
+// sample costs 9 DFMA (recursion 4, output 4, square 1), and splitting time across lanes adds a zero-state pass
+// (4 DFMA) and a state hand-off.  So the design rule is "every sub-partition issues the same number of DFMA":
+//   * one persistent CTA per SM, 8 compute warps = 2 per sub-partition, no producer warp: every warp owns its
+//     streams, its own 3-stage shared-memory ring and its own mbarriers and issues its own TMA box loads
+//     (cp.async.bulk.tensor.3d, SWIZZLE_128B).  Warps never wait for each other inside the main loop.
+//   * 4096 stereo streams over 148 SMs is 6.9 streams per sub-partition.  A warp's time per tile is its segment
+//     length L whatever the number of active lanes, so the two warps of a sub-partition are typed: warp A takes 4
+//     streams x 2 channels x T=4 time segments (L = 80 frames of a 320-frame tile), warp B takes 3 streams x 2 x T=5
+//     (L = 64).  7 streams cost 80 + 64 = 144 sample steps per 320 frames instead of the 2 x 80 a uniform T = 4
+//     layout pays (the round-1 kernel: 7 of 8 warps live, 2-2-2-1 over the sub-partitions).
+//   * per sample the output tap is computed as y / b0 = x + sum (b_i / b0 - a_i) v_i: 4 DFMA instead of 5, the
+//     b0^2 applied once per tile to the partial sum.
+//   * pass 1 of tile t+1 (zero-state recursion, one dependent chain) runs inside the pass-2 loop of tile t.
+//   * after the last tile the CTA's warps gate the completed 100 ms buckets and write the result rows of the
+//     CTA's streams (the code of k_results), so "feed 400 ms, read the meters" is one launch.
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "loudness_results.cuh"
+#include "ssb_internal.cuh"
+#include "tma_ptx.cuh"
+
+namespace ssb {
+
+namespace {
+
+constexpr int kWStages = 3;
+constexpr int kWWarps = 8;  // warps 0..3: type A, warps 4..7: type B; warp w and w+4 share a sub-partition
+
+struct WArgs {
+  double na[5];     // -a[i]
+  double cy[5];     // b[i] / b[0] - a[i]  (cy[0] unused)
+  double b0sq;      // b[0]^2
+  double PA[16];    // D A^LA D, row-major: hand-off of a type-A segment
+  double PB[16];    // D A^LB D
+  double* filt;     // [n][C][4]
+  double* bucket;   // [n][C][kNB]
+  float* speak;     // [n][C]
+  float* tpeak;     // [n][C]
+  float* tphist;    // [n][C][kTpHist]
+  float tp4[3][12];
+  float tp2[24];
+  float2 tp12[12];
+  uint64_t active_mask;
+  unsigned n_streams;
+  unsigned n_tiles;  // tiles of F frames in this launch
+  unsigned s100;
+  unsigned pos0;
+  unsigned slot0;
+  int do_sample_peak;
+  int fused_results;
+};
+
+// One warp type: T time segments of L frames, R streams of C channels; lane = k * (R*C) + row * C + channel.
+template <int C_, int T_, int R_, int L_>
+struct WType {
+  static constexpr int C = C_, T = T_, R = R_, L = L_;
+  static constexpr int Q = R * C;           // lanes per segment
+  static constexpr int F = T * L;           // frames per tile
+  static constexpr int NQ = L * C / 4;      // 16-byte quads per segment
+  static constexpr int FPQ = 4 / C;         // frames per quad
+  static constexpr int U = 16 / FPQ;        // quads per unrolled group (16 frames)
+  static constexpr int NL = F * C / 32;     // 128-byte lines per stream per tile
+  static constexpr unsigned TX_BYTES = R * NL * 128;
+  static constexpr unsigned STAGE_STRIDE = (TX_BYTES + 1023u) / 1024u * 1024u;  // SWIZZLE_128B: 1 KB aligned stages
+  static_assert(Q * T <= 32, "a warp holds all segments of its streams");
+  static_assert(NQ % U == 0, "segments are whole 16-frame groups");
+  static_assert((F * C) % 32 == 0, "tiles are whole 128-byte lines");
+};
+
+template <int C>
+__device__ __forceinline__ float pickc(const float4& q, int f, int c) {
+  if (C == 1) return f == 0 ? q.x : (f == 1 ? q.y : (f == 2 ? q.z : q.w));
+  return f == 0 ? (c ? q.y : q.x) : (c ? q.w : q.z);
+}
+
+// A TMA box {32 floats, R streams, NL lines} lands as [line][stream][128 B]; SWIZZLE_128B XORs the 16-byte chunk
+// index with bits 7..9 of the offset, i.e. with (line * R + stream) & 7.
+template <class W>
+__device__ __forceinline__ const unsigned char* float_addr(const unsigned char* stage, int rr, int fi) {
+  const int qd = fi >> 2;
+  const int rl = (qd >> 3) * W::R + rr;
+  return stage + (rl << 7) + (((qd ^ rl) & 7) << 4) + ((fi & 3) << 2);
+}
+
+__device__ __forceinline__ void to_diff(double v1, double v2, double v3, double v4, double& d0, double& d1, double& d2,
+                                        double& d3) {
+  const double e1 = v1 - v2, e2 = v2 - v3, e3 = v3 - v4;
+  d0 = v1;
+  d1 = e1;
+  d2 = e1 - e2;
+  d3 = (e1 - e2) - (e2 - e3);
+}
+__device__ __forceinline__ void from_diff(double d0, double d1, double d2, double d3, double& v1, double& v2, double& v3,
+                                          double& v4) {
+  const double e2 = d1 - d2;
+  const double e3 = e2 - (d2 - d3);
+  v1 = d0;
+  v2 = d0 - d1;
+  v3 = v2 - e2;
+  v4 = v3 - e3;
+}
+
+#define SSBW_CVT(x) ((double)(x))
+
+// One filter sample: DF-II recursion (newest state last: short dependent chain) + scaled output tap.
+#define SSBW_FILTER_STEP(x)                      \
+  double t_ = fma(a.na[4], v4, (x));             \
+  t_ = fma(a.na[3], v3, t_);                     \
+  t_ = fma(a.na[2], v2, t_);                     \
+  const double v0_ = fma(a.na[1], v1, t_);       \
+  double y_ = fma(a.cy[4], v4, (x));             \
+  y_ = fma(a.cy[3], v3, y_);                     \
+  y_ = fma(a.cy[2], v2, y_);                     \
+  y_ = fma(a.cy[1], v1, y_);                     \
+  v4 = v3; v3 = v2; v2 = v1; v1 = v0_;
+
+#define SSBW_ZERO_STEP(x, z1, z2, z3, z4)        \
+  {                                              \
+    double tz_ = fma(a.na[4], z4, (x));          \
+    tz_ = fma(a.na[3], z3, tz_);                 \
+    tz_ = fma(a.na[2], z2, tz_);                 \
+    const double z0_ = fma(a.na[1], z1, tz_);    \
+    z4 = z3; z3 = z2; z2 = z1; z1 = z0_;         \
+  }
+
+// One true-peak sample: ebur128's polyphase interpolator as f32 FMAs over the register window w2[t] = x[n-1-t]
+// (same tap order in every kernel, so all kernels report identical true peaks).
+#define SSBW_TP_STEP(xf)                                                        \
+  if (TPF == 4) {                                                               \
+    const float2 xx_ = make_float2((xf), (xf));                                 \
+    float2 acc12_ = make_float2((xf) * a.tp12[0].x, (xf) * a.tp12[0].y);        \
+    float acc3_ = (xf) * a.tp4[2][0];                                           \
+    _Pragma("unroll") for (int t = 1; t < 12; t++) {                            \
+      acc12_ = __ffma2_rn(w2[t - 1], a.tp12[t], acc12_);                        \
+      acc3_ = fmaf(w2[t - 1].x, a.tp4[2][t], acc3_);                            \
+    }                                                                           \
+    tp = fmaxf(tp, fmaxf(fabsf(acc12_.x), fmaxf(fabsf(acc12_.y), fabsf(acc3_)))); \
+    _Pragma("unroll") for (int t = TPW - 1; t > 0; t--) w2[t] = w2[t - 1];      \
+    w2[0] = xx_;                                                                \
+  } else if (TPF == 2) {                                                        \
+    float acc_ = (xf) * a.tp2[0];                                               \
+    _Pragma("unroll") for (int t = 1; t < 24; t++) acc_ = fmaf(w2[t - 1].x, a.tp2[t], acc_); \
+    tp = fmaxf(tp, fabsf(acc_));                                                \
+    _Pragma("unroll") for (int t = TPW - 1; t > 0; t--) w2[t] = w2[t - 1];      \
+    w2[0] = make_float2((xf), (xf));                                            \
+  }
+
+// fixed-order sum over the T segments of a chain: ((k0 + k1) + (k2 + k3)) [+ k4]
+template <class W>
+__device__ __forceinline__ double seg_sum(double v, int q) {
+  double s[W::T];
+#pragma unroll
+  for (int k = 0; k < W::T; k++) s[k] = __shfl_sync(0xffffffffu, v, k * W::Q + q);
+  double r = (s[0] + s[1]) + (s[2] + s[3]);
+  if (W::T == 5) r += s[4];
+  return r;
+}
+template <class W>
+__device__ __forceinline__ float seg_max(float v, int q) {
+  float r = 0.f;
+#pragma unroll
+  for (int k = 0; k < W::T; k++) r = fmaxf(r, __shfl_sync(0xffffffffu, v, k * W::Q + q));
+  return r;
+}
+
+// Everything one warp does: for each pass of the CTA over its streams, run this warp's rows through all tiles as ONE
+// continuous software pipeline over 16-frame groups.  Two recursions run in every group iteration:
+//   P1  the zero-state recursion (4 DFMA / sample), LAG = NG + 1 groups ahead (NG groups per tile): when it finishes tile t
+//       its end state z_k(t) is the zero-state response of segment k;
+//   P2  the full filter (9 DFMA / sample) from each segment's true start state.
+// The true states never come out of P2: the carry e(t) (state at the start of tile t, in difference coordinates) is
+// advanced by e <- Pt e + D z_j for j = 0..T-1, lane k keeping e after k steps as its own start state — pure linear
+// algebra on the z's, done in the one group iteration between P1 finishing a tile and P2 starting it.  So there is no
+// pipeline fill or drain at tile boundaries, and the per-tile work (hand-off, bucket sums, TMA refill, mbarrier wait)
+// is a few short blocks between group bodies instead of a dependent chain between two loops.
+template <class W, bool IS_B, int TPF>
+__device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap, unsigned char* stages, uint64_t* full,
+                                         const unsigned cta_row0, const unsigned cta_rows, const unsigned rows_per_pass,
+                                         const unsigned n_pass, const unsigned warp_off, const int lane) {
+  constexpr int C = W::C, T = W::T, Q = W::Q, L = W::L, F = W::F;
+  constexpr int NG = L / 16;        // 16-frame groups per segment = group iterations per tile
+  constexpr int LAG = NG + 1;       // P2 runs this many groups behind P1
+  constexpr int TPW = TPF == 4 ? 11 : (TPF == 2 ? 23 : 1);  // true-peak FIR history length
+  static_assert(L % 16 == 0 && TPW <= L, "segments are whole groups; the FIR history of a segment lies inside the previous one");
+  static_assert(NG <= 8, "mixmask has one bit per group");
+#define SSBW_P(i) (IS_B ? a.PB[i] : a.PA[i])
+
+  // passes in which this warp owns at least one stream (the last pass may be shorter: the count is monotone)
+  unsigned n_task = 0;
+  for (unsigned p = 0; p < n_pass; p++) {
+    const unsigned rp = min(rows_per_pass, cta_rows - p * rows_per_pass);
+    if (rp > warp_off) n_task++;
+  }
+  const unsigned total_tiles = n_task * a.n_tiles;
+  if (total_tiles == 0) return;
+
+  // linear tile counter g = task * n_tiles + tile: ring stage g % 3, barrier phase (g / 3) & 1
+  auto issue = [&](unsigned g) {
+    const unsigned p = g / a.n_tiles, t = g - p * a.n_tiles;
+    const unsigned s = g % kWStages;
+    mbar_expect_tx(&full[s], W::TX_BYTES);
+    tma_load_3d(stages + (size_t)s * W::STAGE_STRIDE, tmap, &full[s], 0,
+                (int)(cta_row0 + p * rows_per_pass + warp_off), (int)(t * W::NL));
+  };
+  if (lane == 0) {
+    for (unsigned g = 0; g < (unsigned)kWStages && g < total_tiles; g++) issue(g);
+  }
+
+  const bool lane_used = lane < T * Q;
+  const int k = lane_used ? lane / Q : 0;
+  const int q = lane_used ? lane - k * Q : 0;
+  const int rr = q / C;
+  const int c = q - rr * C;
+  const int q0 = k * W::NQ;  // first quad of my segment
+
+  // group g of my segment inside a stage: base of its 128-byte line and the swizzle key of its first quad
+#define SSBW_GROUP_ADDR(stage, g, grp, kk)                 \
+  const unsigned char* grp;                                \
+  int kk;                                                  \
+  {                                                        \
+    const int gb_ = q0 + (g) * W::U;                       \
+    const int rl_ = (gb_ >> 3) * W::R + rr;                \
+    grp = (stage) + (rl_ << 7);                            \
+    kk = (gb_ ^ rl_) & 7;                                  \
+  }
+
+  for (unsigned task = 0; task < n_task; task++) {
+    const unsigned rp = min(rows_per_pass, cta_rows - task * rows_per_pass);
+    const unsigned nrows = min((unsigned)W::R, rp - warp_off);
+    const unsigned row_g = cta_row0 + task * rows_per_pass + warp_off;  // first stream of this warp's box
+    const bool row_ok = lane_used && (unsigned)rr < nrows;
+    const bool live = row_ok && ((a.active_mask >> c) & 1ull);
+    const bool owner = row_ok && k == 0;
+    const size_t gidx = ((size_t)(row_g + (row_ok ? rr : 0))) * C + c;
+    const unsigned g0 = task * a.n_tiles;
+
+    // e: the chain's true state at the start of the tile P1 has just finished, in difference coordinates, replicated
+    // in the chain's T lanes; dk: this lane's own start state for that tile
+    double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+    if (live) {
+      const double* f = a.filt + gidx * 4;
+      to_diff(f[0], f[1], f[2], f[3], e0, e1, e2, e3);
+    }
+    double dk0 = 0, dk1 = 0, dk2 = 0, dk3 = 0;
+    double z1 = 0, z2 = 0, z3 = 0, z4 = 0;   // P1: zero-state recursion over my segment of its current tile
+    double v1 = 0, v2 = 0, v3 = 0, v4 = 0;   // P2: the filter state
+    double accA = 0.0, accB = 0.0;           // P2: y^2 / b0^2 of my segment of its current tile, before / after the boundary
+    double acc_cur = 0.0;                    // owner lane: running sum (already times b0^2) of the bucket in progress
+    unsigned slot = a.slot0;
+    if (owner && live && a.pos0 > 0) acc_cur = a.bucket[gidx * kNB + slot];
+    float sp = 0.f, tp = 0.f;
+    float hist[TPW];   // the TPW samples before P2's next tile, hist[t] = x[n-1-t] (meaningful in the k == 0 lanes)
+#pragma unroll
+    for (int t = 0; t < TPW; t++) hist[t] = (TPF >= 2 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
+    float2 w2[TPW];    // P2's FIR window, w2[t] = (x[n-1-t], x[n-1-t]): both halves equal so a tap feeds two phases in one FFMA2
+#pragma unroll
+    for (int t = 0; t < TPW; t++) w2[t] = make_float2(0.f, 0.f);
+    unsigned pos_tile = a.pos0;   // position of P2's current tile start inside the bucket in progress
+    unsigned to_boundary = 0;     // frames of P2's current tile before the bucket boundary (>= F: none inside)
+    int lb = 0;                   // my samples [0, lb) of P2's current tile belong to the bucket in progress
+    unsigned mixmask = 0;         // bit g: some lane of the warp has its boundary strictly inside group g
+
+    const unsigned G = a.n_tiles * NG;
+    unsigned t1 = 0;   // P1's tile
+    int g1 = 0;        // P1's group inside it
+    for (unsigned it = 0; it < G + LAG; it++) {
+      const bool p1_on = it < G, p2_on = it >= (unsigned)LAG;
+      if (g1 == 0) {
+        if (t1 >= 1 && t1 <= a.n_tiles) {
+          // ---- P1 has finished tile t1-1: hand-off in difference coordinates, e <- Pt e + D z_j ----
+          double zd0, zd1, zd2, zd3;
+          to_diff(z1, z2, z3, z4, zd0, zd1, zd2, zd3);
+          z1 = z2 = z3 = z4 = 0.0;
+          if (k == 0) { dk0 = e0; dk1 = e1; dk2 = e2; dk3 = e3; }
+#pragma unroll
+          for (int j = 0; j < T; j++) {
+            const int src = j * Q + q;
+            const double zj0 = __shfl_sync(0xffffffffu, zd0, src), zj1 = __shfl_sync(0xffffffffu, zd1, src);
+            const double zj2 = __shfl_sync(0xffffffffu, zd2, src), zj3 = __shfl_sync(0xffffffffu, zd3, src);
+            const double n0 = fma(SSBW_P(0), e0, fma(SSBW_P(1), e1, fma(SSBW_P(2), e2, fma(SSBW_P(3), e3, zj0))));
+            const double n1 = fma(SSBW_P(4), e0, fma(SSBW_P(5), e1, fma(SSBW_P(6), e2, fma(SSBW_P(7), e3, zj1))));
+            const double n2 = fma(SSBW_P(8), e0, fma(SSBW_P(9), e1, fma(SSBW_P(10), e2, fma(SSBW_P(11), e3, zj2))));
+            const double n3 = fma(SSBW_P(12), e0, fma(SSBW_P(13), e1, fma(SSBW_P(14), e2, fma(SSBW_P(15), e3, zj3))));
+            e0 = n0; e1 = n1; e2 = n2; e3 = n3;
+            if (k == j + 1) { dk0 = n0; dk1 = n1; dk2 = n2; dk3 = n3; }
+          }
+        }
+        if (p1_on) mbar_wait_warp(&full[(g0 + t1) % kWStages], ((g0 + t1) / kWStages) & 1);
+      } else if (g1 == 1 && t1 >= 1) {
+        // ---- P2 starts tile t1-1 from the state the hand-off left in dk ----
+        from_diff(dk0, dk1, dk2, dk3, v1, v2, v3, v4);
+        to_boundary = a.s100 - pos_tile;
+        lb = (int)to_boundary - k * L;
+        lb = lb < 0 ? 0 : (lb > L ? L : lb);
+        mixmask = __reduce_or_sync(0xffffffffu, (lb & 15) ? (1u << (lb >> 4)) : 0u);
+        if (TPF >= 2) {
+          // FIR window: the TPW samples before my segment (previous segment's tail in the same tile, or, for the first
+          // segment, the previous tile's tail carried in `hist`)
+          const unsigned char* st = stages + (size_t)((g0 + t1 - 1) % kWStages) * W::STAGE_STRIDE;
+#pragma unroll
+          for (int t = 0; t < TPW; t++) {
+            const int fr = k > 0 ? k * L - 1 - t : 0;
+            const float prev = *reinterpret_cast<const float*>(float_addr<W>(st, rr, fr * C + c));
+            const float wv = k > 0 ? prev : hist[t];
+            w2[t] = make_float2(wv, wv);
+          }
+        }
+      }
+      const unsigned t2 = g1 >= 1 ? t1 - 1 : t1 - 2;          // P2's tile and group (valid when p2_on)
+      const int g2 = g1 >= 1 ? g1 - 1 : NG - 1;
+      const unsigned char* s1 = stages + (size_t)((g0 + t1) % kWStages) * W::STAGE_STRIDE;
+      const unsigned char* s2 = stages + (size_t)((g0 + t2) % kWStages) * W::STAGE_STRIDE;
+
+      if (p1_on && p2_on && !((mixmask >> g2) & 1u)) {
+        // ---- the steady state: 16 frames of P2 and 16 frames of P1, sample by sample ----
+        SSBW_GROUP_ADDR(s2, g2, grp2, kk2)
+        SSBW_GROUP_ADDR(s1, g1, grp1, kk1)
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < W::U; j++) {
+          const float4 qv = *reinterpret_cast<const float4*>(grp2 + ((kk2 ^ j) << 4));
+          const float4 qn = *reinterpret_cast<const float4*>(grp1 + ((kk1 ^ j) << 4));
+#pragma unroll
+          for (int f = 0; f < W::FPQ; f++) {
+            const float xf = pickc<C>(qv, f, c);
+            if (TPF != 0) sp = fmaxf(sp, fabsf(xf));
+            const double xd = SSBW_CVT(xf);
+            SSBW_FILTER_STEP(xd)
+            acc = fma(y_, y_, acc);
+            SSBW_TP_STEP(xf)
+            const double xn = SSBW_CVT(pickc<C>(qn, f, c));
+            SSBW_ZERO_STEP(xn, z1, z2, z3, z4)
+          }
+        }
+        if (16 * (g2 + 1) <= lb) accA += acc; else accB += acc;
+      } else {
+        // ---- pipeline fill / drain, and groups with a bucket boundary inside: compact loops ----
+        if (p1_on) {
+          SSBW_GROUP_ADDR(s1, g1, grp1, kk1)
+#pragma unroll 1
+          for (int j = 0; j < W::U; j++) {
+            const float4 qn = *reinterpret_cast<const float4*>(grp1 + ((kk1 ^ j) << 4));
+#pragma unroll
+            for (int f = 0; f < W::FPQ; f++) {
+              const double xn = SSBW_CVT(pickc<C>(qn, f, c));
+              SSBW_ZERO_STEP(xn, z1, z2, z3, z4)
+            }
+          }
+        }
+        if (p2_on) {
+          SSBW_GROUP_ADDR(s2, g2, grp2, kk2)
+          int i = 16 * g2;
+#pragma unroll 1
+          for (int j = 0; j < W::U; j++) {
+            const float4 qv = *reinterpret_cast<const float4*>(grp2 + ((kk2 ^ j) << 4));
+#pragma unroll
+            for (int f = 0; f < W::FPQ; f++, i++) {
+              const float xf = pickc<C>(qv, f, c);
+              if (TPF != 0) sp = fmaxf(sp, fabsf(xf));
+              const double xd = SSBW_CVT(xf);
+              SSBW_FILTER_STEP(xd)
+              if (i < lb) accA = fma(y_, y_, accA); else accB = fma(y_, y_, accB);
+              SSBW_TP_STEP(xf)
+            }
+          }
+        }
+      }
+
+      if (p2_on && g2 == NG - 1) {
+        // ---- P2 has finished tile t2: bucket sums (fixed-order reduction over the segments, times b0^2), FIR history,
+        //      and the stage goes back to the TMA ring (the tile three ahead, possibly the next pass's) ----
+        if (TPF >= 2) {
+#pragma unroll
+          for (int t = 0; t < TPW; t++) hist[t] = __shfl_sync(0xffffffffu, w2[t].x, (T - 1) * Q + q);
+        }
+        __syncwarp();
+        if (lane == 0 && g0 + t2 + kWStages < total_tiles) issue(g0 + t2 + kWStages);
+        const double sA = seg_sum<W>(accA, q), sB = seg_sum<W>(accB, q);
+        accA = accB = 0.0;
+        if (k == 0) {
+          acc_cur = fma(a.b0sq, sA, acc_cur);
+          if (to_boundary <= (unsigned)F) {
+            if (owner && live) a.bucket[gidx * kNB + slot] = acc_cur;
+            acc_cur = a.b0sq * sB;
+            slot = (slot + 1) % kNB;
+          }
+        }
+        pos_tile += F;
+        if (pos_tile >= a.s100) pos_tile -= a.s100;
+      }
+      if (++g1 == NG) { g1 = 0; t1++; }
+    }
+
+    // ---------------- end of this warp's streams for this pass: state, bucket in progress, peaks ----------------
+    sp = seg_max<W>(sp, q);
+    tp = seg_max<W>(tp, q);
+    if (owner) {
+      if (live) {
+        a.bucket[gidx * kNB + slot] = acc_cur;
+        double c1, c2, c3, c4;
+        from_diff(e0, e1, e2, e3, c1, c2, c3, c4);   // the carry after the last hand-off: state at the end of the last tile
+        double* f = a.filt + gidx * 4;
+        const double tiny = 2.2250738585072014e-308;  // libebur128: flush denormal state at the end of a call
+        f[0] = fabs(c1) < tiny ? 0.0 : c1;
+        f[1] = fabs(c2) < tiny ? 0.0 : c2;
+        f[2] = fabs(c3) < tiny ? 0.0 : c3;
+        f[3] = fabs(c4) < tiny ? 0.0 : c4;
+      } else {
+        a.bucket[gidx * kNB + slot] = 0.0;
+      }
+      if (TPF != 0) a.speak[gidx] = fmaxf(a.speak[gidx], sp);
+      if (TPF >= 2) {
+        a.tpeak[gidx] = fmaxf(a.tpeak[gidx], tp);
+#pragma unroll
+        for (int t = 0; t < TPW; t++) a.tphist[gidx * kTpHist + t] = hist[t];
+      }
+    }
+  }
+#undef SSBW_GROUP_ADDR
+#undef SSBW_P
+}
+
+// MIXED: type A = (T 4, L 80), type B = (T 5, L 64), 320-frame tiles, 28 stereo streams per pass;
+// !MIXED: every warp (T 4, L 64), 256-frame tiles, 32 stereo streams per pass.
+template <int C, bool MIXED>
+struct WCfg {
+  using A = WType<C, 4, 8 / C, MIXED ? 80 : 64>;
+  using B = WType<C, MIXED ? 5 : 4, (MIXED ? 6 : 8) / C, 64>;
+  static_assert(A::F == B::F, "both warp types walk the same tiles");
+  static constexpr int F = A::F;
+  static constexpr int CAP = 4 * A::R + 4 * B::R;  // streams per CTA pass
+  static constexpr size_t SMEM = (size_t)4 * kWStages * (A::STAGE_STRIDE + B::STAGE_STRIDE) +
+                                 (size_t)kWWarps * kWStages * sizeof(uint64_t) + 1024;
+};
+
+template <int C, int TPF, bool MIXED>
+__global__ void __launch_bounds__(kWWarps * 32, 1)
+k_loudness_wtile(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                 const __grid_constant__ WArgs a, const __grid_constant__ GateParams g,
+                 const __grid_constant__ ResultsArgs ra) {
+  using Cfg = WCfg<C, MIXED>;
+  using WA = typename Cfg::A;
+  using WB = typename Cfg::B;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)4 * kWStages * (WA::STAGE_STRIDE + WB::STAGE_STRIDE));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned n_ctas = gridDim.x;
+  const unsigned row0 = (unsigned)(((unsigned long long)blockIdx.x * a.n_streams) / n_ctas);
+  const unsigned row1 = (unsigned)(((unsigned long long)(blockIdx.x + 1) * a.n_streams) / n_ctas);
+  const unsigned cta_rows = row1 - row0;
+  const unsigned n_pass = (cta_rows + Cfg::CAP - 1) / Cfg::CAP;
+  const unsigned rows_per_pass = n_pass ? (cta_rows + n_pass - 1) / n_pass : 0;
+
+  uint64_t* full = bars + warp * kWStages;
+  if (lane == 0) {
+    for (int s = 0; s < kWStages; s++) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  if (cta_rows) {
+    if (warp < 4) {
+      unsigned char* stages = smem + (size_t)warp * kWStages * WA::STAGE_STRIDE;
+      run_warp<WA, false, TPF>(a, &tmapA, stages, full, row0, cta_rows, rows_per_pass, n_pass, (unsigned)warp * WA::R, lane);
+    } else {
+      unsigned char* stages = smem + (size_t)4 * kWStages * WA::STAGE_STRIDE + (size_t)(warp - 4) * kWStages * WB::STAGE_STRIDE;
+      run_warp<WB, true, TPF>(a, &tmapB, stages, full, row0, cta_rows, rows_per_pass, n_pass,
+                              4u * WA::R + (unsigned)(warp - 4) * WB::R, lane);
+    }
+  }
+  if (a.fused_results) {
+    // gating + result rows of this CTA's streams (analyzer.rs:147-164), one warp per stream; the bucket sums and peaks
+    // written above by other warps of this CTA are visible after the barrier
+    __syncthreads();
+    for (unsigned r = warp; r < cta_rows; r += kWWarps) results_for_stream(g, ra, (size_t)row0 + r, lane);
+  }
+}
+#undef SSBW_FILTER_STEP
+#undef SSBW_ZERO_STEP
+#undef SSBW_TP_STEP
+#undef SSBW_CVT
+
+template <int C, int TPF, bool MIXED>
+cudaError_t launch_cfg(const CUtensorMap& tA, const CUtensorMap& tB, const WArgs& a, const GateParams& g,
+                       const ResultsArgs& ra, unsigned n_ctas, int device, cudaStream_t s) {
+  auto kern = k_loudness_wtile<C, TPF, MIXED>;
+  const size_t smem = WCfg<C, MIXED>::SMEM;
+  static bool configured_dev[64] = {false};  // per instantiation and device
+  bool& configured = configured_dev[device & 63];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    configured = true;
+  }
+  kern<<<n_ctas, kWWarps * 32, smem, s>>>(tA, tB, a, g, ra);
+  return cudaGetLastError();
+}
+
+template <int C, bool MIXED>
+cudaError_t launch_c(const CUtensorMap& tA, const CUtensorMap& tB, const WArgs& a, const GateParams& g,
+                     const ResultsArgs& ra, unsigned n_ctas, int tpf, int device, cudaStream_t s) {
+  if (tpf == 4) return launch_cfg<C, 4, MIXED>(tA, tB, a, g, ra, n_ctas, device, s);
+  if (tpf == 2) return launch_cfg<C, 2, MIXED>(tA, tB, a, g, ra, n_ctas, device, s);
+  if (tpf == 1) return launch_cfg<C, 1, MIXED>(tA, tB, a, g, ra, n_ctas, device, s);
+  return launch_cfg<C, 0, MIXED>(tA, tB, a, g, ra, n_ctas, device, s);
+}
+
+template <class W>
+bool encode_box(CUtensorMap* tm, const float* d_in, size_t n_streams, size_t row_floats, size_t used_floats) {
+  // 3-D view of the [stream][frame][channel] input: dim0 = 32 floats of one 128-byte line, dim1 = stream (row pitch),
+  // dim2 = line index along the row
+  cuuint64_t gdim[3] = {32, (cuuint64_t)n_streams, (cuuint64_t)(used_floats / 32)};
+  cuuint64_t gstride[2] = {(cuuint64_t)(row_floats * sizeof(float)), 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)W::R, (cuuint32_t)W::NL};
+  cuuint32_t estride[3] = {1, 1, 1};
+  return tma_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d_in), gdim, gstride, box, estride,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int C, bool MIXED>
+cudaError_t launch_shape(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames, size_t in_stride_frames,
+                         WArgs& a, const GateParams& g, const ResultsArgs& ra, int sm_count, int device, cudaStream_t s,
+                         size_t* consumed) {
+  using Cfg = WCfg<C, MIXED>;
+  const size_t n_tiles = frames / Cfg::F;
+  if (!n_tiles) return cudaSuccess;
+  const size_t row_floats = in_stride_frames * C;
+  const size_t used_floats = n_tiles * Cfg::F * C;
+  CUtensorMap tA, tB;
+  if (!encode_box<typename Cfg::A>(&tA, d_in, st.n_streams, row_floats, used_floats) ||
+      !encode_box<typename Cfg::B>(&tB, d_in, st.n_streams, row_floats, used_floats))
+    return cudaErrorInvalidValue;
+  memcpy(a.PA, Cfg::A::L == 80 ? p.handoff80 : p.handoff, sizeof(a.PA));   // cached per meter (init_meter)
+  memcpy(a.PB, p.handoff, sizeof(a.PB));
+  static_assert(Cfg::B::L == 64 && (Cfg::A::L == 80 || Cfg::A::L == 64), "hand-off matrices cached for 64 and 80 frames");
+  a.n_tiles = (unsigned)n_tiles;
+  const unsigned n_ctas = (unsigned)(st.n_streams < (size_t)sm_count ? st.n_streams : (size_t)sm_count);
+  // 4 / 2: true-peak FIR (ebur128's rate rule) + sample peak; 1: sample peak only; 0: neither
+  const int tpf = (p.do_true_peak && p.tp_factor) ? p.tp_factor : (p.do_sample_peak ? 1 : 0);
+  cudaError_t e = launch_c<C, MIXED>(tA, tB, a, g, ra, n_ctas, tpf, device, s);
+  if (e) return e;
+  *consumed = n_tiles * Cfg::F;
+  return cudaSuccess;
+}
+
+}  // namespace
+
+int wtile_frames(int variant) { return variant == 1 ? 256 : 320; }
+
+bool wtile_path_usable(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
+                       size_t in_stride_frames, int variant) {
+  if (p.channels < 1 || p.channels > 2) return false;
+  if (st.ring) return false;  // the ring of y is written by the generic / scan kernels
+  const size_t F = (size_t)wtile_frames(variant);
+  if (p.s100 < F || frames < F) return false;
+  if (((uintptr_t)d_in & 15) != 0) return false;
+  if ((in_stride_frames * p.channels * sizeof(float)) % 16 != 0) return false;
+  if (st.n_streams > 0x7fffffffu) return false;
+  return tma_encode_fn() != nullptr;
+}
+
+// Filters the leading floor(frames / F) * F frames of every stream (F = 320, or 256 for variant 1) and, when `ra` is
+// given and the whole chunk was consumed, gates the completed buckets and writes the result rows in the same launch.
+cudaError_t launch_loudness_wtile(const LoudParams& p, const LoudState& st, const GateParams& gp, const float* d_in,
+                                  size_t frames, size_t in_stride_frames, uint32_t pos0, uint64_t bucket0, int variant,
+                                  const ResultsArgs* ra, int sm_count, int device, cudaStream_t s, uint64_t* launches,
+                                  size_t* consumed, bool* results_written) {
+  *consumed = 0;
+  if (results_written) *results_written = false;
+  const int C = p.channels;
+  const size_t F = (size_t)wtile_frames(variant);
+  const bool fuse = ra != nullptr && frames % F == 0;
+  WArgs a{};
+  for (int i = 0; i < 5; i++) {
+    a.na[i] = -p.a[i];
+    // b[i] / b[0] - a[i] rounded ONCE: the taps nearly cancel against states ~1e6 times the output (the high-pass
+    // poles), so a tap that is off by the 4e-16 a plain double division leaves shifts a block energy by ~1e-8 LU at
+    // 96 kHz; with the quotient's remainder carried along the scaled tap agrees with the reference's five-tap form to
+    // the recursion's own rounding noise (1e-11 LU at 48 kHz)
+    const double qh = p.b[i] / p.b[0];
+    const double ql = fma(-qh, p.b[0], p.b[i]) / p.b[0];
+    const double sm = qh - p.a[i];
+    const double bb = sm - qh;
+    const double er = (qh - (sm - bb)) + (-p.a[i] - bb);
+    a.cy[i] = sm + (er + ql);
+  }
+  a.b0sq = p.b[0] * p.b[0];
+  a.filt = st.filt;
+  a.bucket = st.bucket;
+  a.speak = st.speak;
+  a.tpeak = st.tpeak;
+  a.tphist = st.tphist;
+  memcpy(a.tp4, p.tp4, sizeof(a.tp4));
+  memcpy(a.tp2, p.tp2, sizeof(a.tp2));
+  for (int t = 0; t < 12; t++) a.tp12[t] = make_float2(p.tp4[0][t], p.tp4[1][t]);
+  a.active_mask = p.do_filter ? p.active_mask : 0;
+  a.n_streams = (unsigned)st.n_streams;
+  a.s100 = p.s100;
+  a.pos0 = pos0;
+  a.slot0 = (unsigned)(bucket0 % kNB);
+  a.do_sample_peak = p.do_sample_peak;
+  a.fused_results = fuse ? 1 : 0;
+  ResultsArgs none{};
+  const ResultsArgs& r = fuse ? *ra : none;
+  cudaError_t e;
+  if (variant == 1)
+    e = C == 1 ? launch_shape<1, false>(p, st, d_in, frames, in_stride_frames, a, gp, r, sm_count, device, s, consumed)
+               : launch_shape<2, false>(p, st, d_in, frames, in_stride_frames, a, gp, r, sm_count, device, s, consumed);
+  else
+    e = C == 1 ? launch_shape<1, true>(p, st, d_in, frames, in_stride_frames, a, gp, r, sm_count, device, s, consumed)
+               : launch_shape<2, true>(p, st, d_in, frames, in_stride_frames, a, gp, r, sm_count, device, s, consumed);
+  if (e) return e;
+  if (*consumed) {
+    if (launches) ++*launches;
+    if (results_written) *results_written = fuse;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace ssb

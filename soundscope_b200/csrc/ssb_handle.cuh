@@ -13,6 +13,7 @@ struct ssb_analyzer {
   using LoudState = ssb::LoudState;
   using FftPlan = ssb::FftPlan;
   int device = 0;
+  int sm_count = 0;           // multiprocessors of `device` (queried at create; grids are sized from it)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   uint32_t channels = 0, rate = 0;
   int32_t mode = 0;
@@ -32,6 +33,7 @@ struct ssb_analyzer {
   double* d_results = nullptr;
   double* h_results = nullptr;  // pinned
   bool results_valid = false;
+  bool dres_valid = false;      // d_results already holds the rows for the current feed position (fused epilogue)
   bool meter_ok = false;        // false while (re)initialisation failed half-way: every meter call then fails loudly
 
   float* d_stage[2] = {nullptr, nullptr};
@@ -49,7 +51,8 @@ struct ssb_analyzer {
   std::map<std::pair<size_t, uint32_t>, std::pair<std::vector<double>, std::vector<double>>> axes;
 
   uint64_t launches = 0;
-  int force_kernel = 0;  // tests: 0 auto, 1 generic kernel, 2 serial rows kernel, 3 time-segmented tile kernel
+  int force_kernel = 0;  // tests: 0 auto, 1 generic kernel, 2 serial rows kernel, 3 round-1 tile kernel, 4 scan kernel,
+                         // 5 k_loudness_wtile (mixed T4/T5 warps), 6 k_loudness_wtile (uniform T4 warps)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
@@ -95,7 +98,10 @@ int32_t ensure_stage(ssb_analyzer* h, size_t floats);
 int32_t ensure_scratch(ssb_analyzer* h, size_t bytes);          // device scratch + pinned host mirror of the same size
 int32_t ensure_scratch_device(ssb_analyzer* h, size_t bytes);   // device scratch only
 // feed `frames` frames per stream from device memory laid out [stream][in_stride_frames][C]
-int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in_stride_frames);
+// d_results (nullable): where the caller wants the result rows for the position after this feed; *written says
+// whether the filter launch produced them itself (fused epilogue) — otherwise the caller launches k_results
+int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in_stride_frames,
+                    double* d_results = nullptr, bool* written = nullptr);
 int32_t get_plan(ssb_analyzer* h, size_t n, uint32_t rate, FftPlan** out);
 int32_t fft_shape_check(size_t n, uint32_t rate);
 // launches k_results for stream rows (gating pending buckets first) and leaves them in h->d_results; no copy

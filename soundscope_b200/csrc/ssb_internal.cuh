@@ -31,7 +31,8 @@ struct LoudParams {
   uint32_t s100;        // samples_in_100ms
   int do_filter, do_sample_peak, do_true_peak;
   uint64_t active_mask; // bit c set: channel c is not Channel::Unused
-  double handoff[16];   // D A^64 D: segment hand-off matrix of the time-segmented kernel (tile_handoff_matrix)
+  double handoff[16];   // D A^64 D: segment hand-off matrix of the time-segmented kernels (tile_handoff_matrix)
+  double handoff80[16]; // D A^80 D: the 80-frame segments of k_loudness_wtile's type-A warps
 };
 
 struct GateParams {
@@ -44,7 +45,7 @@ struct GateParams {
 // --- host-side tables (host_tables.cu) ---------------------------------------------------------
 void kweight_coeffs(uint32_t rate, double b[5], double a[5]);
 void default_channel_weights(uint32_t channels, float w[kMaxChannels], uint64_t* active_mask);
-int truepeak_taps(uint32_t rate, float tp4[3][12], float tp2[24]);   // returns factor 0/2/4
+int truepeak_taps(uint32_t rate, float tp4[3][12], float tp2[24], int force_factor = 0);   // returns factor 0/2/4
 void histogram_tables(double energies[1000], double boundaries[1001]);
 float libm_cosf(float x);                                            // libm 0.2.16 (musl) cosf
 void hann_multipliers(size_t n, std::vector<float>& w);             // spectrum-analyzer hann_window
@@ -68,6 +69,66 @@ struct LoudState {
   const double* hist_boundaries;  // [1001]
 };
 
+// Arguments of the per-stream result / gating code (loudness_results.cuh): k_results and the fused epilogue of
+// k_loudness_wtile take the same struct.
+struct ResultsArgs {
+  const double* bucket;          // [n][C][kNB]
+  const uint32_t* block_hist;    // [n][1000] (read through L2 after the gating atomics)
+  const uint32_t* st_hist;
+  uint32_t* block_hist_rw;
+  uint32_t* st_hist_rw;
+  const float* speak;
+  const float* tpeak;
+  const double* ring;            // or nullptr
+  size_t ring_frames, ring_pos;
+  const double* ring_e;          // [n][2] from k_ring_energy, or nullptr
+  const double* energies;        // [1000] bin-centre energies
+  const double* bounds;          // [1001] bin boundaries
+  uint64_t buckets_done;
+  int aligned, mode;
+  double* out;                   // [n][4 + 2C]
+  uint64_t gate_first, gate_last;  // buckets to enter into the histograms first (none when gate_last < gate_first)
+};
+
+inline ResultsArgs make_results_args(const LoudState& st, uint64_t buckets_done, int aligned, size_t ring_pos, int mode,
+                                     double* d_out, uint64_t gate_first, uint64_t gate_last, const double* ring_e) {
+  ResultsArgs ra{};
+  ra.bucket = st.bucket;
+  ra.block_hist = st.block_hist;
+  ra.st_hist = st.st_hist;
+  ra.block_hist_rw = st.block_hist;
+  ra.st_hist_rw = st.st_hist;
+  ra.speak = st.speak;
+  ra.tpeak = st.tpeak;
+  ra.ring = st.ring;
+  ra.ring_frames = st.ring_frames;
+  ra.ring_pos = ring_pos;
+  ra.ring_e = ring_e;
+  ra.energies = st.hist_energies;
+  ra.bounds = st.hist_boundaries;
+  ra.buckets_done = buckets_done;
+  ra.aligned = aligned;
+  ra.mode = mode;
+  ra.out = d_out;
+  ra.gate_first = gate_first;
+  ra.gate_last = gate_last;
+  return ra;
+}
+
+
+// Second-generation batch kernel (loudness_wtile.cu): mono / stereo, no ring; variant 0 = mixed T4/T5 warps on 320-frame
+// tiles, variant 1 = uniform T4 warps on 256-frame tiles.  Consumes the leading whole tiles; with `ra` and a chunk of
+// whole tiles it also gates the completed buckets and writes the result rows (*results_written).
+int wtile_frames(int variant);
+bool wtile_path_usable(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
+                       size_t in_stride_frames, int variant);
+cudaError_t launch_loudness_wtile(const LoudParams& p, const LoudState& st, const GateParams& gp, const float* d_in,
+                                  size_t frames, size_t in_stride_frames, uint32_t pos0, uint64_t bucket0, int variant,
+                                  const ResultsArgs* ra, int sm_count, int device, cudaStream_t s, uint64_t* launches,
+                                  size_t* consumed, bool* results_written);
+// stream count from which the serial many-streams kernel replaces the time-segmented ones (SSB_SERIAL_MIN overrides)
+size_t serial_min_streams();
+
 // Filters `frames` frames per stream starting `pos0` frames into 100 ms bucket number `bucket0`.
 // At most kMaxBucketsPerLaunch buckets may complete inside one call.
 cudaError_t launch_loudness_generic(const LoudParams& p, const LoudState& st, const float* d_in,
@@ -79,7 +140,7 @@ bool tile_path_usable(const LoudParams& p, const LoudState& st, const float* d_i
                       size_t in_stride_frames);
 cudaError_t launch_loudness_tile(const LoudParams& p, const LoudState& st, const float* d_in, size_t frames,
                                  size_t in_stride_frames, uint32_t pos0, uint64_t bucket0, cudaStream_t s,
-                                 uint64_t* launches, size_t* consumed, int force_kernel);
+                                 uint64_t* launches, size_t* consumed, int force_kernel, int sm_count);
 // D A^64 D for the K-weighting denominator a[] (double-double on the host, rounded once); cached in LoudParams
 void tile_handoff_matrix(const double a[5], double P[16]);
 // D A^n D for any n (loudness_tile.cu); the scan kernel's table holds n = 64 m, m = 0..32
@@ -108,6 +169,7 @@ cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t bu
                            size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches,
                            uint64_t gate_first, uint64_t gate_last);
 cudaError_t launch_reset(const LoudState& st, int channels, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_histogram_index(const LoudState& st, const double* d_e, size_t n, int32_t* d_out, cudaStream_t s);
 
 // --- kernel launchers (spectrum.cu) ------------------------------------------------------------
 struct FftPlan {

@@ -62,3 +62,28 @@ def test_ebu3341_true_peak(ssb, cuda):
         a.add_samples(np.repeat(x.astype(np.float32)[:, None], 2, 1).ravel())
         tp_db = 20 * np.log10(a.get_true_peak()[0])
         assert -6.4 <= tp_db <= -5.8, (phase_deg, tp_db)
+
+
+def test_histogram_bin_edges_g5(ssb, oracle, cuda):
+    """SURVEY section 8c, golden set G5: block energies placed on, and 1-2 ulp either side of, every one of the 1001
+    histogram boundaries (and on the bin centres, and log-uniform random ones) land in the bin the crate's bisection
+    picks.  The gating kernels reach the index from a closed-form guess corrected against the boundary table
+    (csrc/loudness_results.cuh find_histogram_index); one wrong edge decision moves a stream's integrated loudness by
+    ~0.1 LU / n_blocks, so this is asserted exactly."""
+    b = ssb.BatchAnalyzer(1, 2, 48000, ssb.MODE_ALL)
+    bounds = np.array([oracle.histogram_boundary(i) for i in range(1001)])
+    centres = np.array([oracle.histogram_energy(i) for i in range(1000)])
+    cases = [bounds, centres]
+    for k in (1, 2, 3):
+        up, dn = bounds.copy(), bounds.copy()
+        for _ in range(k):
+            up, dn = np.nextafter(up, np.inf), np.nextafter(dn, -np.inf)
+        cases += [up, dn]
+    rng = np.random.default_rng(5)
+    cases.append(10.0 ** rng.uniform(-8.0, 4.0, 200000))           # -80 .. +40 dB re full scale: below the gate and past the top bin
+    cases.append(np.array([bounds[0] * 0.5, bounds[1000], bounds[1000] * 4.0, 1e300, 5e-324, 0.0]))
+    e = np.concatenate(cases)
+    got = b.histogram_index(e)
+    want = np.array([oracle.find_histogram_index(x) if x >= bounds[0] else -1 for x in e], dtype=np.int32)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, (e[bad[:5]], got[bad[:5]], want[bad[:5]])

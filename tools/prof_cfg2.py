@@ -9,9 +9,13 @@ mode = S.MODE_ALL if "--all" in sys.argv else S.MODE_LOUDNESS
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
 an = S.BatchAnalyzer(N_STREAMS, CHANNELS, RATE, mode, device=0)
+an.force_kernel(int(os.environ.get('FORCE', 0)))
 xs = [make_input_device(torch, N_STREAMS, FRAMES, 1234 + i, dev) for i in range(2)]
 for i in range(6):
-    an.add_frames_device(xs[i & 1])
+    if os.environ.get('NOFUSE'):
+        an.add_frames_device(xs[i & 1])
+    else:
+        res = an.add_frames_results_device(xs[i & 1])
 res = an.results_device()
 torch.cuda.synchronize()
 if "--fft" in sys.argv:

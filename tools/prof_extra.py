@@ -36,7 +36,7 @@ for i in range(3):
     single.analyze_microphone_input(ring)
 print("done")
 # whole-file one-shot (file-mode k_loudness_scan + k_file_gating) on a 60 s stereo file
-from tests.signals import sweep_stereo
+from soundscope_b200.synth import sweep_stereo
 whole = np.tile(sweep_stereo(10.0, 48000), 6)
 for i in range(2):
     single.calculate_integrated_lufs(2, whole)

@@ -3,7 +3,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import soundscope_b200 as S
-from tests.signals import sweep_stereo
+from soundscope_b200.synth import sweep_stereo
 
 a = S.Analyzer()
 a.create_loudness_meter(2, 48000)
