@@ -132,6 +132,26 @@ int32_t ssb_results_device(ssb_analyzer* h, double* d_out);
  * ssb_results_device.  Asynchronous. */
 int32_t ssb_add_frames_f32_device_results(ssb_analyzer* h, const float* d_interleaved, size_t frames_per_stream,
                                           double* d_out);
+/* ---- multi-GPU: the gather of the per-stream result rows -------------------------------
+ * Streams are independent (every meter's state is private to its EbuR128, analyzer.rs:29-32), so ranks own disjoint
+ * blocks of streams and the only exchange is the gather of the result rows.  Here the kernel that computes a rank's
+ * rows also stores them into block `rank` of EVERY rank's gather buffer (peer memory over NVLink, mapped with CUDA
+ * IPC) — no collective kernel.  All ranks use the same n_streams / channels.  Protocol:
+ *   ssb_gather_create(h, world, rank, handle64)   allocate; returns this rank's 64-byte IPC handle
+ *   (exchange the handles through your process group)
+ *   ssb_gather_open(h, handles)                   handles = world x 64 bytes in rank order (own slot ignored)
+ *   ... every ssb_results_device / ssb_add_frames_f32_device_results now also publishes into parity `p` ...
+ *   ssb_gather_wait(h)                            enqueue: until every rank's publish count has reached this rank's
+ *   ssb_gather_rows(h, p)                         DEVICE pointer to [world * n_streams][ssb_result_stride] f64
+ *   ssb_gather_select(h, p ^ 1)                   next publishes go to the other half while `p` is read */
+int32_t ssb_gather_create(ssb_analyzer* h, uint32_t world, uint32_t rank, void* ipc_handle_out);
+int32_t ssb_gather_open(ssb_analyzer* h, const void* ipc_handles);
+int32_t ssb_gather_select(ssb_analyzer* h, int32_t parity);
+double* ssb_gather_rows(ssb_analyzer* h, int32_t parity);
+uint64_t ssb_gather_epoch(const ssb_analyzer* h);
+int32_t ssb_gather_wait(ssb_analyzer* h);
+int32_t ssb_gather_destroy(ssb_analyzer* h);
+
 /* Analyzer::calculate_integrated_lufs (analyzer.rs:170-182): a fresh meter at the handle's rate over the whole
  * interleaved file; a `sample_rate*2`-sample chunk that is not whole frames (or an invalid channel count) gives
  * *is_some = 0, the reference's `None`.  The reference builds the meter with Mode::all() but reads nothing except

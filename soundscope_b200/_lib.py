@@ -53,7 +53,8 @@ SYMBOLS = [
     "ssb_true_peak", "ssb_sample_peak", "ssb_get_true_peak", "ssb_result_stride", "ssb_results_device",
     "ssb_calculate_integrated_lufs", "ssb_get_fft", "ssb_fft_bins", "ssb_fft_axis", "ssb_fft_batch_device",
     "ssb_process_tick", "ssb_preanalyze_file", "ssb_get_waveform", "ssb_waveform_device", "ssb_mid_side", "ssb_mid_side_device", "ssb_filter_coeffs",
-    "ssb_histograms", "ssb_profile_enable", "ssb_profile_read", "ssb_debug_force_generic", "ssb_true_peak_factor", "ssb_debug_force_true_peak_factor", "ssb_debug_histogram_index",
+    "ssb_histograms", "ssb_profile_enable", "ssb_profile_read", "ssb_debug_force_generic", "ssb_gather_create", "ssb_gather_open", "ssb_gather_select", "ssb_gather_rows", "ssb_gather_epoch", "ssb_gather_wait", "ssb_gather_destroy",
+    "ssb_true_peak_factor", "ssb_debug_force_true_peak_factor", "ssb_debug_histogram_index",
     "ssb_pcm_bytes_per_sample", "ssb_pcm_to_f32", "ssb_pcm_to_f32_device", "ssb_add_frames_pcm", "ssb_add_frames_pcm_device",
     "ssb_capture_ring_create", "ssb_capture_ring_destroy", "ssb_capture_ring_capacity", "ssb_capture_ring_written",
     "ssb_capture_ring_push", "ssb_capture_ring_to_vec", "ssb_mic_tick",
@@ -105,6 +106,13 @@ def lib():
         "ssb_result_stride": (C.c_size_t, [vp]),
         "ssb_results_device": (C.c_int32, [vp, f64p]),
         "ssb_debug_histogram_index": (C.c_int32, [vp, f64p, C.c_size_t, vp]),
+        "ssb_gather_create": (C.c_int32, [vp, C.c_uint32, C.c_uint32, vp]),
+        "ssb_gather_open": (C.c_int32, [vp, vp]),
+        "ssb_gather_select": (C.c_int32, [vp, C.c_int32]),
+        "ssb_gather_rows": (C.c_void_p, [vp, C.c_int32]),
+        "ssb_gather_epoch": (C.c_uint64, [vp]),
+        "ssb_gather_wait": (C.c_int32, [vp]),
+        "ssb_gather_destroy": (C.c_int32, [vp]),
         "ssb_true_peak_factor": (C.c_int32, [vp]),
         "ssb_debug_force_true_peak_factor": (C.c_int32, [vp, C.c_int32]),
         "ssb_calculate_integrated_lufs": (C.c_int32, [vp, C.c_uint32, f32p, C.c_size_t, C.POINTER(C.c_double), i32p]),

@@ -133,6 +133,41 @@ class BatchAnalyzer:
         check(self._h, lib().ssb_pcm_to_f32_device(self._h, C.c_void_p(raw.data_ptr()), n, code, C.c_void_p(out.data_ptr())))
         return out
 
+    # ---- multi-GPU gather of the result rows (include/soundscope_b200.h, "multi-GPU") ----------------
+    def gather_create(self, world, rank):
+        """-> this rank's 64-byte CUDA IPC handle of its gather buffer"""
+        buf = C.create_string_buffer(64)
+        check(self._h, lib().ssb_gather_create(self._h, world, rank, buf))
+        return bytes(buf.raw)
+
+    def gather_open(self, handles):
+        """handles: world x 64 bytes in rank order (own slot ignored)"""
+        check(self._h, lib().ssb_gather_open(self._h, C.c_char_p(handles)))
+
+    def gather_select(self, parity):
+        check(self._h, lib().ssb_gather_select(self._h, int(parity)))
+
+    def gather_wait(self):
+        check(self._h, lib().ssb_gather_wait(self._h))
+
+    def gather_epoch(self):
+        return lib().ssb_gather_epoch(self._h)
+
+    def gather_rows(self, parity, world):
+        """[world * n_streams, stride] f64 CUDA tensor aliasing half `parity` of this rank's gather buffer"""
+        import torch
+        ptr = lib().ssb_gather_rows(self._h, int(parity))
+        if not ptr:
+            raise SsbError(3, "no gather buffer")
+        n = world * self.n_streams * self.stride
+
+        class _Mem:   # __cuda_array_interface__ view of library-owned memory (the handle outlives the tensor's use)
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Mem(), device="cuda").view(world * self.n_streams, self.stride)
+
+    def gather_destroy(self):
+        check(self._h, lib().ssb_gather_destroy(self._h))
+
     def results_device(self, out=None):
         """[n_streams, 4+2C] f64 CUDA tensor: momentary, shortterm, integrated, LRA, true_peak[C], sample_peak[C]."""
         import torch

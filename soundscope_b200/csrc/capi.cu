@@ -204,12 +204,14 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
         const bool pending = done_after > h->gated_upto;
         ra = make_results_args(h->st, done_after, (frames_after % s100) == 0, h->ring_pos, h->mode, d_results,
                                pending ? h->gated_upto : 1, pending ? done_after - 1 : 0, nullptr);
+        ra.ga = peek_gather_args(h);   // rows also go to every rank's gather buffer when one is open
         rap = &ra;
       }
       bool wrote = false;
       CK(launch_loudness_wtile(h->lp, h->st, h->gp, d_in + done * C, n, in_stride_frames, pos, bucket0, wvariant, rap,
                                h->sm_count, h->device, h->stream, &h->launches, &tiled, &wrote));
       if (wrote) {
+        if (ra.ga.world) h->gather.epoch++;
         if (done_after > h->gated_upto) h->gated_upto = done_after;
         if (written) *written = true;
       }
@@ -232,8 +234,10 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
 int32_t launch_results_now(ssb_analyzer* h) {
   const int aligned = (h->total_frames % h->lp.s100) == 0;
   const uint64_t done = h->total_frames / h->lp.s100;
+  const GatherArgs ga = peek_gather_args(h);
   CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, h->d_results, h->stream, &h->launches,
-                    done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0));
+                    done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0, ga.world ? &ga : nullptr));
+  if (ga.world) h->gather.epoch++;
   if (done > h->gated_upto) h->gated_upto = done;
   return SSB_OK;
 }
@@ -397,6 +401,7 @@ void ssb_analyzer_destroy(ssb_analyzer* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->oneshot) ssb_analyzer_destroy(h->oneshot);
   h->oneshot = nullptr;
+  ssb_gather_destroy(h);
   free_meter(h);
   cudaFree(h->d_hist_tables);
   for (int i = 0; i < 2; i++) {
@@ -621,8 +626,10 @@ int32_t ssb_results_device(ssb_analyzer* h, double* d_out) {
   const int aligned = (h->total_frames % h->lp.s100) == 0;
   {
     const uint64_t done = h->total_frames / h->lp.s100;
+    const GatherArgs ga = peek_gather_args(h);
     CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, d_out, h->stream, &h->launches,
-                      done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0));
+                      done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0, ga.world ? &ga : nullptr));
+    if (ga.world) h->gather.epoch++;
     if (done > h->gated_upto) h->gated_upto = done;
   }
   return SSB_OK;

@@ -251,13 +251,13 @@ __global__ void __launch_bounds__(128, 4)
 k_results(const __grid_constant__ GateParams g, const __grid_constant__ ResultsArgs ra, size_t n_streams) {
   const size_t s = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (s >= n_streams) return;
-  results_for_stream(g, ra, s, lane);
+  if (s < n_streams) results_for_stream(g, ra, s, lane);
+  gather_block_done(ra.ga);
 }
 
 cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
                            size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches,
-                           uint64_t gate_first, uint64_t gate_last) {
+                           uint64_t gate_first, uint64_t gate_last, const GatherArgs* ga) {
   if (!st.n_streams) return cudaSuccess;
   const double* ring_e = nullptr;
   if (st.ring && st.ring_e) {
@@ -268,8 +268,13 @@ cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t bu
   }
   const int tpb = 128;
   const size_t threads = st.n_streams * 32;
-  const ResultsArgs ra = make_results_args(st, buckets_done, aligned, ring_pos, mode, d_out, gate_first, gate_last, ring_e);
-  k_results<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, s>>>(g, ra, st.n_streams);
+  ResultsArgs ra = make_results_args(st, buckets_done, aligned, ring_pos, mode, d_out, gate_first, gate_last, ring_e);
+  const unsigned blocks = (unsigned)((threads + tpb - 1) / tpb);
+  if (ga) {
+    ra.ga = *ga;
+    ra.ga.n_blocks = blocks;
+  }
+  k_results<<<blocks, tpb, 0, s>>>(g, ra, st.n_streams);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

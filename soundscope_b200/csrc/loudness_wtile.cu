@@ -159,6 +159,11 @@ __device__ __forceinline__ void from_diff(double d0, double d1, double d2, doubl
 // fixed-order sum over the T segments of a chain: ((k0 + k1) + (k2 + k3)) [+ k4]
 template <class W>
 __device__ __forceinline__ double seg_sum(double v, int q) {
+  if (W::T == 4 && W::Q == 8) {   // lanes k * 8 + q: two butterfly rounds give every lane (k0 + k1) + (k2 + k3)
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+  }
   double s[W::T];
 #pragma unroll
   for (int k = 0; k < W::T; k++) s[k] = __shfl_sync(0xffffffffu, v, k * W::Q + q);
@@ -174,26 +179,25 @@ __device__ __forceinline__ float seg_max(float v, int q) {
   return r;
 }
 
-// Everything one warp does: for each pass of the CTA over its streams, run this warp's rows through all tiles as ONE
-// continuous software pipeline over 16-frame groups.  Two recursions run in every group iteration:
-//   P1  the zero-state recursion (4 DFMA / sample), LAG = NG + 1 groups ahead (NG groups per tile): when it finishes tile t
-//       its end state z_k(t) is the zero-state response of segment k;
-//   P2  the full filter (9 DFMA / sample) from each segment's true start state.
-// The true states never come out of P2: the carry e(t) (state at the start of tile t, in difference coordinates) is
-// advanced by e <- Pt e + D z_j for j = 0..T-1, lane k keeping e after k steps as its own start state — pure linear
-// algebra on the z's, done in the one group iteration between P1 finishing a tile and P2 starting it.  So there is no
-// pipeline fill or drain at tile boundaries, and the per-tile work (hand-off, bucket sums, TMA refill, mbarrier wait)
-// is a few short blocks between group bodies instead of a dependent chain between two loops.
+// Everything one warp does: for each pass of the CTA over its streams, run this warp's rows through all tiles.
+// Two recursions run side by side in every 16-frame group of the main loop:
+//   P2  the full filter (9 DFMA / sample) over tile t from each segment's true start state;
+//   P1  the zero-state recursion (4 DFMA / sample), one tile AND one group ahead: groups 1..NG-1 of tile t+1 during
+//       groups 0..NG-2 of P2, then group 0 of tile t+2 during P2's last group.
+// The true states never come out of P2: the carry e (state at a tile start, in difference coordinates) is advanced by
+// e <- Pt e + D z_j for j = 0..T-1, lane k keeping e after k steps as its own start state — linear algebra on P1's
+// end states only.  Because P1 is one group ahead, z(t+1) is complete before P2's last group of tile t, and the
+// hand-off for tile t+1 sits in the same straight-line block as that group: its shuffles and dependent DFMA chains
+// fill the issue gaps of the 16 sample steps instead of standing between two loops.
 template <class W, bool IS_B, int TPF>
 __device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap, unsigned char* stages, uint64_t* full,
                                          const unsigned cta_row0, const unsigned cta_rows, const unsigned rows_per_pass,
                                          const unsigned n_pass, const unsigned warp_off, const int lane) {
   constexpr int C = W::C, T = W::T, Q = W::Q, L = W::L, F = W::F;
-  constexpr int NG = L / 16;        // 16-frame groups per segment = group iterations per tile
-  constexpr int LAG = NG + 1;       // P2 runs this many groups behind P1
+  constexpr int NG = L / 16;        // 16-frame groups per segment
   constexpr int TPW = TPF == 4 ? 11 : (TPF == 2 ? 23 : 1);  // true-peak FIR history length
   static_assert(L % 16 == 0 && TPW <= L, "segments are whole groups; the FIR history of a segment lies inside the previous one");
-  static_assert(NG <= 8, "mixmask has one bit per group");
+  static_assert(NG >= 2 && NG <= 8, "mixmask has one bit per group");
 #define SSBW_P(i) (IS_B ? a.PB[i] : a.PA[i])
 
   // passes in which this warp owns at least one stream (the last pass may be shorter: the count is monotone)
@@ -234,6 +238,87 @@ __device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap
     grp = (stage) + (rl_ << 7);                            \
     kk = (gb_ ^ rl_) & 7;                                  \
   }
+  // hand-off in difference coordinates from P1's end state of a finished tile: e <- Pt e + D z_j, j = 0..T-1; lane k
+  // keeps e after k steps (its segment's start state); after T steps e is the state at the start of the next tile.
+  // BEGIN captures D z and clears P1's state; STEP(j) is one link of the chain (4 shuffled doubles, a 4x4 mat-vec).
+#define SSBW_HO_BEGIN(commit)                                                                                        \
+  double zd0, zd1, zd2, zd3;                                                                                         \
+  to_diff(z1, z2, z3, z4, zd0, zd1, zd2, zd3);                                                                       \
+  z1 = z2 = z3 = z4 = 0.0;                                                                                           \
+  if ((commit) && k == 0) { dk0 = e0; dk1 = e1; dk2 = e2; dk3 = e3; }
+#define SSBW_HO_STEP(j, commit)                                                                                      \
+  {                                                                                                                  \
+    const int src = (j) * Q + q;                                                                                     \
+    const double zj0 = __shfl_sync(0xffffffffu, zd0, src), zj1 = __shfl_sync(0xffffffffu, zd1, src);                 \
+    const double zj2 = __shfl_sync(0xffffffffu, zd2, src), zj3 = __shfl_sync(0xffffffffu, zd3, src);                 \
+    const double n0 = fma(SSBW_P(0), e0, fma(SSBW_P(1), e1, fma(SSBW_P(2), e2, fma(SSBW_P(3), e3, zj0))));          \
+    const double n1 = fma(SSBW_P(4), e0, fma(SSBW_P(5), e1, fma(SSBW_P(6), e2, fma(SSBW_P(7), e3, zj1))));          \
+    const double n2 = fma(SSBW_P(8), e0, fma(SSBW_P(9), e1, fma(SSBW_P(10), e2, fma(SSBW_P(11), e3, zj2))));        \
+    const double n3 = fma(SSBW_P(12), e0, fma(SSBW_P(13), e1, fma(SSBW_P(14), e2, fma(SSBW_P(15), e3, zj3))));      \
+    if (commit) {                                                                                                    \
+      e0 = n0; e1 = n1; e2 = n2; e3 = n3;                                                                            \
+      if (k == (j) + 1) { dk0 = n0; dk1 = n1; dk2 = n2; dk3 = n3; }                                                  \
+    }                                                                                                                \
+  }
+#define SSBW_HANDOFF(commit)                                                        \
+  {                                                                                 \
+    SSBW_HO_BEGIN(commit)                                                           \
+    _Pragma("unroll") for (int j_ = 0; j_ < T; j_++) SSBW_HO_STEP(j_, commit)       \
+  }
+#define SSBW_NOHOOK(j)
+  // one hand-off link after each of the first T quads of the group (the hooks are resolved at compile time)
+#define SSBW_HO_HOOK(j) if ((j) < T) SSBW_HO_STEP(j, has1)
+  // 16 frames of P2 (stage s2, group g2) and 16 frames of P1 (stage s1, group g1), sample by sample
+#define SSBW_FUSED_GROUP(s2, g2, s1, g1, HOOK)                                                 \
+  {                                                                                         \
+    SSBW_GROUP_ADDR(s2, g2, grp2, kk2)                                                      \
+    SSBW_GROUP_ADDR(s1, g1, grp1, kk1)                                                      \
+    double acc = 0.0;                                                                       \
+    _Pragma("unroll") for (int j = 0; j < W::U; j++) {                                      \
+      const float4 qv = *reinterpret_cast<const float4*>(grp2 + ((kk2 ^ j) << 4));          \
+      const float4 qn = *reinterpret_cast<const float4*>(grp1 + ((kk1 ^ j) << 4));          \
+      _Pragma("unroll") for (int f = 0; f < W::FPQ; f++) {                                  \
+        const float xf = pickc<C>(qv, f, c);                                                \
+        if (TPF != 0) sp = fmaxf(sp, fabsf(xf));                                            \
+        const double xd = SSBW_CVT(xf);                                                     \
+        SSBW_FILTER_STEP(xd)                                                                \
+        acc = fma(y_, y_, acc);                                                             \
+        SSBW_TP_STEP(xf)                                                                    \
+        const double xn = SSBW_CVT(pickc<C>(qn, f, c));                                     \
+        SSBW_ZERO_STEP(xn, z1, z2, z3, z4)                                                  \
+      }                                                                                     \
+      HOOK(j)                                                                               \
+    }                                                                                       \
+    if (16 * ((g2) + 1) <= lb) accA += acc; else accB += acc;                               \
+  }
+  // compact (rolled) forms for the pipeline fill and for tiles with a bucket boundary inside a group
+#define SSBW_P1_GROUP(s1, g1)                                                               \
+  {                                                                                         \
+    SSBW_GROUP_ADDR(s1, g1, grp1, kk1)                                                      \
+    _Pragma("unroll 1") for (int j = 0; j < W::U; j++) {                                    \
+      const float4 qn = *reinterpret_cast<const float4*>(grp1 + ((kk1 ^ j) << 4));          \
+      _Pragma("unroll") for (int f = 0; f < W::FPQ; f++) {                                  \
+        const double xn = SSBW_CVT(pickc<C>(qn, f, c));                                     \
+        SSBW_ZERO_STEP(xn, z1, z2, z3, z4)                                                  \
+      }                                                                                     \
+    }                                                                                       \
+  }
+#define SSBW_P2_GROUP(s2, g2)                                                               \
+  {                                                                                         \
+    SSBW_GROUP_ADDR(s2, g2, grp2, kk2)                                                      \
+    int i_ = 16 * (g2);                                                                     \
+    _Pragma("unroll 1") for (int j = 0; j < W::U; j++) {                                    \
+      const float4 qv = *reinterpret_cast<const float4*>(grp2 + ((kk2 ^ j) << 4));          \
+      _Pragma("unroll") for (int f = 0; f < W::FPQ; f++, i_++) {                            \
+        const float xf = pickc<C>(qv, f, c);                                                \
+        if (TPF != 0) sp = fmaxf(sp, fabsf(xf));                                            \
+        const double xd = SSBW_CVT(xf);                                                     \
+        SSBW_FILTER_STEP(xd)                                                                \
+        if (i_ < lb) accA = fma(y_, y_, accA); else accB = fma(y_, y_, accB);               \
+        SSBW_TP_STEP(xf)                                                                    \
+      }                                                                                     \
+    }                                                                                       \
+  }
 
   for (unsigned task = 0; task < n_task; task++) {
     const unsigned rp = min(rows_per_pass, cta_rows - task * rows_per_pass);
@@ -244,9 +329,11 @@ __device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap
     const bool owner = row_ok && k == 0;
     const size_t gidx = ((size_t)(row_g + (row_ok ? rr : 0))) * C + c;
     const unsigned g0 = task * a.n_tiles;
+#define SSBW_STAGE(tile) (stages + (size_t)((g0 + (tile)) % kWStages) * W::STAGE_STRIDE)
+#define SSBW_WAIT(tile) mbar_wait_warp(&full[(g0 + (tile)) % kWStages], ((g0 + (tile)) / kWStages) & 1)
 
-    // e: the chain's true state at the start of the tile P1 has just finished, in difference coordinates, replicated
-    // in the chain's T lanes; dk: this lane's own start state for that tile
+    // e: the chain's true state at a tile start, in difference coordinates, replicated in the chain's T lanes;
+    // dk: this lane's own start state for the tile P2 is about to run
     double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
     if (live) {
       const double* f = a.filt + gidx * 4;
@@ -255,7 +342,6 @@ __device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap
     double dk0 = 0, dk1 = 0, dk2 = 0, dk3 = 0;
     double z1 = 0, z2 = 0, z3 = 0, z4 = 0;   // P1: zero-state recursion over my segment of its current tile
     double v1 = 0, v2 = 0, v3 = 0, v4 = 0;   // P2: the filter state
-    double accA = 0.0, accB = 0.0;           // P2: y^2 / b0^2 of my segment of its current tile, before / after the boundary
     double acc_cur = 0.0;                    // owner lane: running sum (already times b0^2) of the bucket in progress
     unsigned slot = a.slot0;
     if (owner && live && a.pos0 > 0) acc_cur = a.bucket[gidx * kNB + slot];
@@ -263,143 +349,96 @@ __device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap
     float hist[TPW];   // the TPW samples before P2's next tile, hist[t] = x[n-1-t] (meaningful in the k == 0 lanes)
 #pragma unroll
     for (int t = 0; t < TPW; t++) hist[t] = (TPF >= 2 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
-    float2 w2[TPW];    // P2's FIR window, w2[t] = (x[n-1-t], x[n-1-t]): both halves equal so a tap feeds two phases in one FFMA2
-#pragma unroll
-    for (int t = 0; t < TPW; t++) w2[t] = make_float2(0.f, 0.f);
     unsigned pos_tile = a.pos0;   // position of P2's current tile start inside the bucket in progress
-    unsigned to_boundary = 0;     // frames of P2's current tile before the bucket boundary (>= F: none inside)
-    int lb = 0;                   // my samples [0, lb) of P2's current tile belong to the bucket in progress
-    unsigned mixmask = 0;         // bit g: some lane of the warp has its boundary strictly inside group g
 
-    const unsigned G = a.n_tiles * NG;
-    unsigned t1 = 0;   // P1's tile
-    int g1 = 0;        // P1's group inside it
-    for (unsigned it = 0; it < G + LAG; it++) {
-      const bool p1_on = it < G, p2_on = it >= (unsigned)LAG;
-      if (g1 == 0) {
-        if (t1 >= 1 && t1 <= a.n_tiles) {
-          // ---- P1 has finished tile t1-1: hand-off in difference coordinates, e <- Pt e + D z_j ----
-          double zd0, zd1, zd2, zd3;
-          to_diff(z1, z2, z3, z4, zd0, zd1, zd2, zd3);
-          z1 = z2 = z3 = z4 = 0.0;
-          if (k == 0) { dk0 = e0; dk1 = e1; dk2 = e2; dk3 = e3; }
+    // ---- pipeline fill: P1 over the whole first tile, its hand-off, P1's first group of the second tile ----
+    SSBW_WAIT(0);
+    {
+      const unsigned char* st = SSBW_STAGE(0);
+#pragma unroll 1
+      for (int g = 0; g < NG; g++) SSBW_P1_GROUP(st, g)
+    }
+    SSBW_HANDOFF(true)
+    if (a.n_tiles > 1) {
+      SSBW_WAIT(1);
+      const unsigned char* st = SSBW_STAGE(1);
+      SSBW_P1_GROUP(st, 0)
+    }
+
+    for (unsigned tile = 0; tile < a.n_tiles; tile++) {
+      const bool has1 = tile + 1 < a.n_tiles, has2 = tile + 2 < a.n_tiles;
+      const unsigned char* st0 = SSBW_STAGE(tile);
+      // ---- P2 starts the tile from the state the hand-off left in dk ----
+      from_diff(dk0, dk1, dk2, dk3, v1, v2, v3, v4);
+      const unsigned to_boundary = a.s100 - pos_tile;  // frames of this tile before the bucket boundary (>= F: none inside)
+      int lb = (int)to_boundary - k * L;               // my samples [0, lb) belong to the bucket in progress
+      lb = lb < 0 ? 0 : (lb > L ? L : lb);
+      const unsigned mixed = __reduce_or_sync(0xffffffffu, (unsigned)(lb & 15));  // a boundary strictly inside a group
+      double accA = 0.0, accB = 0.0;
+      // FIR window: the TPW samples before my segment (previous segment's tail in the same tile, or, for the first
+      // segment, the previous tile's tail carried in `hist`); both halves equal so a tap feeds two phases in one FFMA2
+      float2 w2[TPW];
+      if (TPF >= 2) {
 #pragma unroll
-          for (int j = 0; j < T; j++) {
-            const int src = j * Q + q;
-            const double zj0 = __shfl_sync(0xffffffffu, zd0, src), zj1 = __shfl_sync(0xffffffffu, zd1, src);
-            const double zj2 = __shfl_sync(0xffffffffu, zd2, src), zj3 = __shfl_sync(0xffffffffu, zd3, src);
-            const double n0 = fma(SSBW_P(0), e0, fma(SSBW_P(1), e1, fma(SSBW_P(2), e2, fma(SSBW_P(3), e3, zj0))));
-            const double n1 = fma(SSBW_P(4), e0, fma(SSBW_P(5), e1, fma(SSBW_P(6), e2, fma(SSBW_P(7), e3, zj1))));
-            const double n2 = fma(SSBW_P(8), e0, fma(SSBW_P(9), e1, fma(SSBW_P(10), e2, fma(SSBW_P(11), e3, zj2))));
-            const double n3 = fma(SSBW_P(12), e0, fma(SSBW_P(13), e1, fma(SSBW_P(14), e2, fma(SSBW_P(15), e3, zj3))));
-            e0 = n0; e1 = n1; e2 = n2; e3 = n3;
-            if (k == j + 1) { dk0 = n0; dk1 = n1; dk2 = n2; dk3 = n3; }
-          }
-        }
-        if (p1_on) mbar_wait_warp(&full[(g0 + t1) % kWStages], ((g0 + t1) / kWStages) & 1);
-      } else if (g1 == 1 && t1 >= 1) {
-        // ---- P2 starts tile t1-1 from the state the hand-off left in dk ----
-        from_diff(dk0, dk1, dk2, dk3, v1, v2, v3, v4);
-        to_boundary = a.s100 - pos_tile;
-        lb = (int)to_boundary - k * L;
-        lb = lb < 0 ? 0 : (lb > L ? L : lb);
-        mixmask = __reduce_or_sync(0xffffffffu, (lb & 15) ? (1u << (lb >> 4)) : 0u);
-        if (TPF >= 2) {
-          // FIR window: the TPW samples before my segment (previous segment's tail in the same tile, or, for the first
-          // segment, the previous tile's tail carried in `hist`)
-          const unsigned char* st = stages + (size_t)((g0 + t1 - 1) % kWStages) * W::STAGE_STRIDE;
-#pragma unroll
-          for (int t = 0; t < TPW; t++) {
-            const int fr = k > 0 ? k * L - 1 - t : 0;
-            const float prev = *reinterpret_cast<const float*>(float_addr<W>(st, rr, fr * C + c));
-            const float wv = k > 0 ? prev : hist[t];
-            w2[t] = make_float2(wv, wv);
-          }
+        for (int t = 0; t < TPW; t++) {
+          const int fr = k > 0 ? k * L - 1 - t : 0;
+          const float prev = *reinterpret_cast<const float*>(float_addr<W>(st0, rr, fr * C + c));
+          const float wv = k > 0 ? prev : hist[t];
+          w2[t] = make_float2(wv, wv);
         }
       }
-      const unsigned t2 = g1 >= 1 ? t1 - 1 : t1 - 2;          // P2's tile and group (valid when p2_on)
-      const int g2 = g1 >= 1 ? g1 - 1 : NG - 1;
-      const unsigned char* s1 = stages + (size_t)((g0 + t1) % kWStages) * W::STAGE_STRIDE;
-      const unsigned char* s2 = stages + (size_t)((g0 + t2) % kWStages) * W::STAGE_STRIDE;
-
-      if (p1_on && p2_on && !((mixmask >> g2) & 1u)) {
-        // ---- the steady state: 16 frames of P2 and 16 frames of P1, sample by sample ----
-        SSBW_GROUP_ADDR(s2, g2, grp2, kk2)
-        SSBW_GROUP_ADDR(s1, g1, grp1, kk1)
-        double acc = 0.0;
+      if (!mixed) {
+        // ---- the steady state.  Without a next tile P1 reruns over this one and its result is dropped. ----
+        const unsigned char* s1 = has1 ? SSBW_STAGE(tile + 1) : st0;
+#pragma unroll 1
+        for (int g = 0; g < NG - 1; g++) SSBW_FUSED_GROUP(st0, g, s1, g + 1, SSBW_NOHOOK)
+        if (has2) SSBW_WAIT(tile + 2);
+        const unsigned char* s2n = has2 ? SSBW_STAGE(tile + 2) : st0;
+        // P1 has finished tile + 1: its hand-off is threaded through P2's last group, one link per quad
+        SSBW_HO_BEGIN(has1)
+        SSBW_FUSED_GROUP(st0, NG - 1, s2n, 0, SSBW_HO_HOOK)
 #pragma unroll
-        for (int j = 0; j < W::U; j++) {
-          const float4 qv = *reinterpret_cast<const float4*>(grp2 + ((kk2 ^ j) << 4));
-          const float4 qn = *reinterpret_cast<const float4*>(grp1 + ((kk1 ^ j) << 4));
-#pragma unroll
-          for (int f = 0; f < W::FPQ; f++) {
-            const float xf = pickc<C>(qv, f, c);
-            if (TPF != 0) sp = fmaxf(sp, fabsf(xf));
-            const double xd = SSBW_CVT(xf);
-            SSBW_FILTER_STEP(xd)
-            acc = fma(y_, y_, acc);
-            SSBW_TP_STEP(xf)
-            const double xn = SSBW_CVT(pickc<C>(qn, f, c));
-            SSBW_ZERO_STEP(xn, z1, z2, z3, z4)
-          }
-        }
-        if (16 * (g2 + 1) <= lb) accA += acc; else accB += acc;
+        for (int j_ = W::U; j_ < T; j_++) SSBW_HO_STEP(j_, has1)   // mono: 4 quads per group, up to 5 links
       } else {
-        // ---- pipeline fill / drain, and groups with a bucket boundary inside: compact loops ----
-        if (p1_on) {
-          SSBW_GROUP_ADDR(s1, g1, grp1, kk1)
 #pragma unroll 1
-          for (int j = 0; j < W::U; j++) {
-            const float4 qn = *reinterpret_cast<const float4*>(grp1 + ((kk1 ^ j) << 4));
-#pragma unroll
-            for (int f = 0; f < W::FPQ; f++) {
-              const double xn = SSBW_CVT(pickc<C>(qn, f, c));
-              SSBW_ZERO_STEP(xn, z1, z2, z3, z4)
-            }
+        for (int g = 0; g < NG; g++) {
+          SSBW_P2_GROUP(st0, g)
+          if (has1 && g < NG - 1) {
+            const unsigned char* s1 = SSBW_STAGE(tile + 1);
+            SSBW_P1_GROUP(s1, g + 1)
           }
         }
-        if (p2_on) {
-          SSBW_GROUP_ADDR(s2, g2, grp2, kk2)
-          int i = 16 * g2;
-#pragma unroll 1
-          for (int j = 0; j < W::U; j++) {
-            const float4 qv = *reinterpret_cast<const float4*>(grp2 + ((kk2 ^ j) << 4));
-#pragma unroll
-            for (int f = 0; f < W::FPQ; f++, i++) {
-              const float xf = pickc<C>(qv, f, c);
-              if (TPF != 0) sp = fmaxf(sp, fabsf(xf));
-              const double xd = SSBW_CVT(xf);
-              SSBW_FILTER_STEP(xd)
-              if (i < lb) accA = fma(y_, y_, accA); else accB = fma(y_, y_, accB);
-              SSBW_TP_STEP(xf)
-            }
-          }
+        SSBW_HANDOFF(has1)
+        if (has2) {
+          SSBW_WAIT(tile + 2);
+          const unsigned char* s2n = SSBW_STAGE(tile + 2);
+          SSBW_P1_GROUP(s2n, 0)
         }
       }
+      if (!has2) { z1 = z2 = z3 = z4 = 0.0; }   // nothing real ran in P1's last group
 
-      if (p2_on && g2 == NG - 1) {
-        // ---- P2 has finished tile t2: bucket sums (fixed-order reduction over the segments, times b0^2), FIR history,
-        //      and the stage goes back to the TMA ring (the tile three ahead, possibly the next pass's) ----
-        if (TPF >= 2) {
+      // ---- P2 has finished the tile: FIR history, stage back to the TMA ring (the tile three ahead, possibly the next
+      //      pass's), bucket sums (fixed-order reduction over the segments, times b0^2) ----
+      if (TPF >= 2) {
 #pragma unroll
-          for (int t = 0; t < TPW; t++) hist[t] = __shfl_sync(0xffffffffu, w2[t].x, (T - 1) * Q + q);
-        }
-        __syncwarp();
-        if (lane == 0 && g0 + t2 + kWStages < total_tiles) issue(g0 + t2 + kWStages);
-        const double sA = seg_sum<W>(accA, q), sB = seg_sum<W>(accB, q);
-        accA = accB = 0.0;
+        for (int t = 0; t < TPW; t++) hist[t] = __shfl_sync(0xffffffffu, w2[t].x, (T - 1) * Q + q);
+      }
+      __syncwarp();
+      if (lane == 0 && g0 + tile + kWStages < total_tiles) issue(g0 + tile + kWStages);
+      const double sA = seg_sum<W>(accA, q);
+      if (to_boundary <= (unsigned)F) {
+        const double sB = seg_sum<W>(accB, q);
         if (k == 0) {
           acc_cur = fma(a.b0sq, sA, acc_cur);
-          if (to_boundary <= (unsigned)F) {
-            if (owner && live) a.bucket[gidx * kNB + slot] = acc_cur;
-            acc_cur = a.b0sq * sB;
-            slot = (slot + 1) % kNB;
-          }
+          if (owner && live) a.bucket[gidx * kNB + slot] = acc_cur;
+          acc_cur = a.b0sq * sB;
+          slot = (slot + 1) % kNB;
         }
-        pos_tile += F;
-        if (pos_tile >= a.s100) pos_tile -= a.s100;
+      } else if (k == 0) {
+        acc_cur = fma(a.b0sq, sA, acc_cur);
       }
-      if (++g1 == NG) { g1 = 0; t1++; }
+      pos_tile += F;
+      if (pos_tile >= a.s100) pos_tile -= a.s100;
     }
 
     // ---------------- end of this warp's streams for this pass: state, bucket in progress, peaks ----------------
@@ -426,8 +465,18 @@ __device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap
         for (int t = 0; t < TPW; t++) a.tphist[gidx * kTpHist + t] = hist[t];
       }
     }
+#undef SSBW_STAGE
+#undef SSBW_WAIT
   }
 #undef SSBW_GROUP_ADDR
+#undef SSBW_HANDOFF
+#undef SSBW_HO_BEGIN
+#undef SSBW_HO_STEP
+#undef SSBW_NOHOOK
+#undef SSBW_HO_HOOK
+#undef SSBW_FUSED_GROUP
+#undef SSBW_P1_GROUP
+#undef SSBW_P2_GROUP
 #undef SSBW_P
 }
 
@@ -486,6 +535,7 @@ k_loudness_wtile(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     // written above by other warps of this CTA are visible after the barrier
     __syncthreads();
     for (unsigned r = warp; r < cta_rows; r += kWWarps) results_for_stream(g, ra, (size_t)row0 + r, lane);
+    gather_block_done(ra.ga);
   }
 }
 #undef SSBW_FILTER_STEP
@@ -615,7 +665,9 @@ cudaError_t launch_loudness_wtile(const LoudParams& p, const LoudState& st, cons
   a.do_sample_peak = p.do_sample_peak;
   a.fused_results = fuse ? 1 : 0;
   ResultsArgs none{};
-  const ResultsArgs& r = fuse ? *ra : none;
+  ResultsArgs mine = fuse ? *ra : none;
+  mine.ga.n_blocks = (unsigned)(st.n_streams < (size_t)sm_count ? st.n_streams : (size_t)sm_count);   // the grid of launch_shape
+  const ResultsArgs& r = mine;
   cudaError_t e;
   if (variant == 1)
     e = C == 1 ? launch_shape<1, false>(p, st, d_in, frames, in_stride_frames, a, gp, r, sm_count, device, s, consumed)

@@ -50,6 +50,15 @@ struct ssb_analyzer {
   std::map<std::pair<size_t, uint32_t>, FftPlan> plans;
   std::map<std::pair<size_t, uint32_t>, std::pair<std::vector<double>, std::vector<double>>> axes;
 
+  struct Gather {
+    void* base = nullptr;                        // [2][world][n][stride] f64 rows | flags[world] u64 (at +rows_bytes) | counter (at +rows_bytes+128)
+    void* peer_base[ssb::kMaxGatherRanks] = {};  // every rank's allocation as mapped here (own = base)
+    size_t rows_bytes = 0;
+    int world = 0, rank = 0, parity = 0;
+    bool open = false;
+    unsigned long long epoch = 0;                // publishes so far
+  } gather;
+
   uint64_t launches = 0;
   int force_kernel = 0;  // tests: 0 auto, 1 generic kernel, 2 serial rows kernel, 3 round-1 tile kernel, 4 scan kernel,
                          // 5 k_loudness_wtile (mixed T4/T5 warps), 6 k_loudness_wtile (uniform T4 warps)
@@ -92,6 +101,10 @@ struct DeviceGuard {
     if (prev >= 0) cudaSetDevice(prev);
   }
 };
+
+// gather.cu: GatherArgs the next results launch would publish with (world == 0 when no gather is open); the caller
+// increments h->gather.epoch when that launch is enqueued
+GatherArgs peek_gather_args(ssb_analyzer* h);
 
 // capi.cu
 int32_t ensure_stage(ssb_analyzer* h, size_t floats);

@@ -71,6 +71,17 @@ struct LoudState {
 
 // Arguments of the per-stream result / gating code (loudness_results.cuh): k_results and the fused epilogue of
 // k_loudness_wtile take the same struct.
+// Publication of the result rows to every rank's gather buffer (gather.cu); world <= 1: none
+constexpr int kMaxGatherRanks = 8;
+struct GatherArgs {
+  int world, rank;
+  double* rows[kMaxGatherRanks];                // per destination rank: block `rank` of the selected parity
+  unsigned long long* flags[kMaxGatherRanks];   // per destination rank: its flag word for `rank`
+  unsigned long long epoch;                     // this publish's number
+  unsigned* counter;                            // local: CTAs of the launch that are done
+  unsigned n_blocks;                            // CTAs in the launch (set by the launcher)
+};
+
 struct ResultsArgs {
   const double* bucket;          // [n][C][kNB]
   const uint32_t* block_hist;    // [n][1000] (read through L2 after the gating atomics)
@@ -88,6 +99,7 @@ struct ResultsArgs {
   int aligned, mode;
   double* out;                   // [n][4 + 2C]
   uint64_t gate_first, gate_last;  // buckets to enter into the histograms first (none when gate_last < gate_first)
+  GatherArgs ga;                   // zero unless a gather is open on the handle
 };
 
 inline ResultsArgs make_results_args(const LoudState& st, uint64_t buckets_done, int aligned, size_t ring_pos, int mode,
@@ -167,7 +179,7 @@ cudaError_t launch_gating(const GateParams& g, const LoudState& st, uint64_t j_f
 // [gate_first, gate_last] (none when gate_last < gate_first) are gated inside the same launch first.
 cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
                            size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches,
-                           uint64_t gate_first, uint64_t gate_last);
+                           uint64_t gate_first, uint64_t gate_last, const GatherArgs* ga = nullptr);
 cudaError_t launch_reset(const LoudState& st, int channels, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_histogram_index(const LoudState& st, const double* d_e, size_t n, int32_t* d_out, cudaStream_t s);
 

@@ -41,3 +41,89 @@ def gather_results(local_rows, n_streams, group=None):
     if all(s == pad for s in sizes):
         return out
     return torch.cat([out[r * pad: r * pad + sizes[r]] for r in range(world)], dim=0)
+
+
+class PeerGather:
+    """The gather of a BatchAnalyzer's result rows over all ranks, for one rank.
+
+    kind "p2p": every results launch of the analyzer also stores this rank's rows into every rank's gather buffer
+    (CUDA IPC peer memory over NVLink, include/soundscope_b200.h "multi-GPU") — no collective kernel; `wait()`
+    enqueues the arrival check and flips the double buffer.  kind "nccl": the fallback when peer mapping is not
+    available — one all_gather_into_tensor of the latest rows per `wait()`.
+
+        g = PeerGather(an, world, rank)            # collective: every rank constructs it
+        an.add_frames_results_device(x, g.local_rows())    # any number of times
+        rows = g.wait()                            # [world * n_streams, stride], rows of every rank's latest launch
+    """
+
+    def __init__(self, an, env=None, world=None, rank=None, group=None, allow_p2p=True):
+        import torch
+        import torch.distributed as dist
+        self.an, self.group = an, group
+        self.world = world if world is not None else (env.world if env is not None else dist.get_world_size(group))
+        self.rank = rank if rank is not None else (env.rank if env is not None else dist.get_rank(group))
+        self._local = torch.empty((an.n_streams, an.stride), dtype=torch.float64, device="cuda")
+        self.parity = 0
+        self.kind = "nccl all_gather_into_tensor per wait()"
+        self._all = None
+        ok = 0
+        if allow_p2p and self.world <= 8:
+            try:
+                handle = an.gather_create(self.world, self.rank)
+                ok = 1
+            except Exception:
+                handle = bytes(64)
+        else:
+            handle = bytes(64)
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (ok, handle), group=group)
+        else:
+            handles = [(ok, handle)]
+        if all(h[0] for h in handles):
+            try:
+                an.gather_open(b"".join(h[1] for h in handles))
+                opened = 1
+            except Exception:
+                opened = 0
+        else:
+            opened = 0
+        if self.world > 1:
+            flags = [None] * self.world
+            dist.all_gather_object(flags, opened, group=group)
+        else:
+            flags = [opened]
+        if all(flags):
+            self.kind = "p2p: result rows stored into every rank's buffer by the results epilogue (CUDA IPC over NVLink), no collective kernel"
+            self._p2p = True
+            an.gather_select(0)
+        else:
+            self._p2p = False
+            if ok:
+                an.gather_destroy()
+            self._all = torch.empty((self.world * an.n_streams, an.stride), dtype=torch.float64, device="cuda")
+
+    def local_rows(self):
+        return self._local
+
+    def publish(self):
+        """p2p: the results launch has already published; nccl: the rows travel in wait()."""
+        return None
+
+    def wait(self):
+        """Rows of every rank's latest results launch, [world * n_streams, stride], valid in stream order."""
+        import torch.distributed as dist
+        if self._p2p:
+            self.an.gather_wait()
+            rows = self.an.gather_rows(self.parity, self.world)
+            self.parity ^= 1
+            self.an.gather_select(self.parity)   # the next launches fill the other half while this one is read
+            return rows
+        dist.all_gather_into_tensor(self._all, self._local, group=self.group)
+        return self._all
+
+    def close(self):
+        if self._p2p:
+            self.an.sync()
+            self.an.gather_destroy()
+            self._p2p = False

@@ -1,7 +1,7 @@
 #!/bin/bash
 # k_loudness_wtile on the GPU: parity tests, A/B timing, ncu captures (filter only, and with the fused epilogue)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_wtile.py -m gpu -q -s -x > gpurun_out/wt_pytest.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_wtile.py tests/test_gpu_ebu.py -m gpu -q -s -x > gpurun_out/wt_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/wt_pytest.log
 timeout 300 python tools/time_wtile.py > gpurun_out/wt_time.log 2>&1
 NOFUSE=1 FORCE=5 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_loudness_wtile -s 3 -c 1 \
