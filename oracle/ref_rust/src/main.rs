@@ -29,6 +29,16 @@ impl Out {
             name, shape, off
         ));
     }
+    fn f32s(&mut self, name: &str, v: &[f32]) {
+        let off = self.bin.len();
+        for x in v {
+            self.bin.extend_from_slice(&x.to_le_bytes());
+        }
+        self.index.push(format!(
+            "\"{}\": {{\"dtype\": \"f4\", \"shape\": [{}], \"offset\": {}}}",
+            name, v.len(), off
+        ));
+    }
     fn pairs(&mut self, name: &str, v: &[(f64, f64)]) {
         let flat: Vec<f64> = v.iter().flat_map(|p| [p.0, p.1]).collect();
         self.f64s(name, &[v.len(), 2], &flat);
@@ -98,14 +108,18 @@ fn main() {
     // ---- G1: the six analyzer tests' own inputs (analyzer.rs:191-385) ----
     for (name, f) in [("g1_fft_440", 440.0f32), ("g1_fft_bin372", 372.0 * 44100.0 / 16384.0), ("g1_fft_125", 46.0 * 44100.0 / 16384.0)] {
         let a = Analyzer::default();
-        o.pairs(name, &a.get_fft(&ref_sine(f, 16384, 44100.0, 1.0)).unwrap());
+        let x = ref_sine(f, 16384, 44100.0, 1.0);
+        o.f32s(&format!("{name}_in"), &x); // f32 sin is the platform libm's: the input travels with the output
+        o.pairs(name, &a.get_fft(&x).unwrap());
     }
     {
         let s: Vec<f32> = (0..44100).map(|i| (i as f32 / 44100.0).sin()).collect();
+        o.f32s("g1_waveform_in", &s);
         o.pairs("g1_waveform", &Analyzer::get_waveform(&s, 15.0));
         let mut a = Analyzer::default();
         let x: Vec<f32> = (0..88200).map(|i| 0.1 * (440.0 * 2.0 * std::f32::consts::PI * (i as f32 / 44100.0)).sin()).collect();
         a.add_samples(&x).unwrap();
+        o.f32s("g1_loudness_in", &x);
         o.f64s("g1_loudness", &[5], &loudness_row(&mut a));
     }
 
@@ -121,7 +135,7 @@ fn main() {
         while pos <= x.len() {
             a.add_samples(&x[pos - 16384..pos]).unwrap(); // tui.rs:1528-1543: overlapping windows, as the player feeds them
             rows.extend(loudness_row(&mut a));
-            if hop % 32 == 0 {
+            if hop % 32 == 0 && pos / 2 >= 16384 {
                 let p = pos / 2;
                 o.pairs(&format!("{tag}_mid_fft_{hop}"), &a.get_fft(&mid[p - 16384..p]).unwrap());
                 o.pairs(&format!("{tag}_side_fft_{hop}"), &a.get_fft(&side[p - 16384..p]).unwrap());

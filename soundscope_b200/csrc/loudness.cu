@@ -11,6 +11,8 @@
 // State layout in HBM (all stream-major):
 //   filt[n][C][4] f64 | bucket[n][C][64] f64 | block_hist[n][1000] u32 | st_hist[n][1000] u32
 //   speak/tpeak[n][C] f32 | tphist[n][C][24] f32 | ring[n][ring_frames][C] f64 (optional)
+#include <stdlib.h>
+
 #include "loudness_results.cuh"
 
 namespace ssb {
@@ -247,11 +249,15 @@ k_ring_energy(const GateParams g, const double* __restrict__ ring, size_t ring_f
   }
 }
 
-__global__ void __launch_bounds__(128, 4)
+template <int V>
+__global__ void __launch_bounds__(128, V == 2 ? 4 : 1)
 k_results(const __grid_constant__ GateParams g, const __grid_constant__ ResultsArgs ra, size_t n_streams) {
   const size_t s = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (s < n_streams) results_for_stream(g, ra, s, lane);
+  if (s < n_streams) {
+    if (V == 0) results_for_stream_v0(g, ra, s, lane);
+    else results_for_stream(g, ra, s, lane);
+  }
   gather_block_done(ra.ga);
 }
 
@@ -274,7 +280,11 @@ cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t bu
     ra.ga = *ga;
     ra.ga.n_blocks = blocks;
   }
-  k_results<<<blocks, tpb, 0, s>>>(g, ra, st.n_streams);
+  // SSB_RESULTS_V: 0 = round-1 ordering, 1 = loads first (default), 2 = loads first capped at 128 registers (A/B timing)
+  static const int variant = [] { const char* e = getenv("SSB_RESULTS_V"); return e ? atoi(e) : 1; }();
+  if (variant == 0) k_results<0><<<blocks, tpb, 0, s>>>(g, ra, st.n_streams);
+  else if (variant == 2) k_results<2><<<blocks, tpb, 0, s>>>(g, ra, st.n_streams);
+  else k_results<1><<<blocks, tpb, 0, s>>>(g, ra, st.n_streams);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -35,7 +35,9 @@ namespace ssb {
 namespace {
 
 constexpr int kWStages = 3;
-constexpr int kWWarps = 8;  // warps 0..3: type A, warps 4..7: type B; warp w and w+4 share a sub-partition
+constexpr int kWPairs = 8;  // sets of streams per CTA: 0..3 type A, 4..7 type B; every set has a P2 warp and a P1 warp
+constexpr int kWWarps = 16;
+constexpr int kWBars = 5;   // per pair: TMA full x 3, dk_full, dk_free
 
 struct WArgs {
   double na[5];     // -a[i]
@@ -179,33 +181,140 @@ __device__ __forceinline__ float seg_max(float v, int q) {
   return r;
 }
 
-// Everything one warp does: for each pass of the CTA over its streams, run this warp's rows through all tiles.
-// Two recursions run side by side in every 16-frame group of the main loop:
-//   P2  the full filter (9 DFMA / sample) over tile t from each segment's true start state;
-//   P1  the zero-state recursion (4 DFMA / sample), one tile AND one group ahead: groups 1..NG-1 of tile t+1 during
-//       groups 0..NG-2 of P2, then group 0 of tile t+2 during P2's last group.
-// The true states never come out of P2: the carry e (state at a tile start, in difference coordinates) is advanced by
-// e <- Pt e + D z_j for j = 0..T-1, lane k keeping e after k steps as its own start state — linear algebra on P1's
-// end states only.  Because P1 is one group ahead, z(t+1) is complete before P2's last group of tile t, and the
-// hand-off for tile t+1 sits in the same straight-line block as that group: its shuffles and dependent DFMA chains
-// fill the issue gaps of the 16 sample steps instead of standing between two loops.
-template <class W, bool IS_B, int TPF>
-__device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap, unsigned char* stages, uint64_t* full,
-                                         const unsigned cta_row0, const unsigned cta_rows, const unsigned rows_per_pass,
-                                         const unsigned n_pass, const unsigned warp_off, const int lane) {
+// ------------------------------------------------------------------------------------------------------------------
+// Two warps per set of streams, specialised by pass, reading the same shared-memory tiles:
+//   the P1 warp runs the zero-state recursion (4 DFMA / sample) over every tile as soon as it lands, then the hand-off:
+//       the carry e (state at the tile start, in difference coordinates) advances by e <- Pt e + D z_j, j = 0..T-1, lane
+//       k keeping e after k steps as its segment's start state — linear algebra on the zero-state end states only, so
+//       the true states never have to come out of the full filter — and publishes the start states through a
+//       1 KB shared-memory slot (mbarrier dk_full / dk_free);
+//   the P2 warp picks the start states up, runs the full filter (9 DFMA / sample, + peaks), sums the buckets and hands
+//       the stage back to the TMA ring.
+// Four warps per sub-partition (P1 and P2 of a type-A and of a type-B set) progress independently: while one is in
+// its per-tile serial work (hand-off chain, reductions, barrier waits, TMA issue) the others keep the FP64 pipe busy.
+// The first generation of this kernel ran both passes in one warp (two warps per sub-partition) and lost a quarter of
+// every warp's time to that serial work (profiles/r2_wtile_v1.md).
+// ------------------------------------------------------------------------------------------------------------------
+struct PairGeom {
+  unsigned cta_row0, cta_rows, rows_per_pass, n_pass, warp_off;
+};
+
+template <class W>
+__device__ __forceinline__ unsigned count_tasks(const PairGeom& gm) {
+  // passes in which this pair owns at least one stream (the last pass may be shorter: the count is monotone)
+  unsigned n_task = 0;
+  for (unsigned p = 0; p < gm.n_pass; p++) {
+    const unsigned rp = min(gm.rows_per_pass, gm.cta_rows - p * gm.rows_per_pass);
+    if (rp > gm.warp_off) n_task++;
+  }
+  return n_task;
+}
+
+// group g of my segment inside a stage: base of its 128-byte line and the swizzle key of its first quad
+#define SSBW_GROUP_ADDR(stage, g, grp, kk)                 \
+  const unsigned char* grp;                                \
+  int kk;                                                  \
+  {                                                        \
+    const int gb_ = q0 + (g) * W::U;                       \
+    const int rl_ = (gb_ >> 3) * W::R + rr;                \
+    grp = (stage) + (rl_ << 7);                            \
+    kk = (gb_ ^ rl_) & 7;                                  \
+  }
+
+template <class W, bool IS_B>
+__device__ __forceinline__ void run_p1(const WArgs& a, unsigned char* stages, uint64_t* full, uint64_t* dk_full,
+                                       uint64_t* dk_free, double* dk_slot, const PairGeom gm, const int lane) {
+  constexpr int C = W::C, T = W::T, Q = W::Q, L = W::L;
+  constexpr int NG = L / 16;
+#define SSBW_P(i) (IS_B ? a.PB[i] : a.PA[i])
+  const unsigned n_task = count_tasks<W>(gm);
+  if (n_task * a.n_tiles == 0) return;
+  const bool lane_used = lane < T * Q;
+  const int k = lane_used ? lane / Q : 0;
+  const int q = lane_used ? lane - k * Q : 0;
+  const int rr = q / C;
+  const int c = q - rr * C;
+  const int q0 = k * W::NQ;  // first quad of my segment
+
+  for (unsigned task = 0; task < n_task; task++) {
+    const unsigned rp = min(gm.rows_per_pass, gm.cta_rows - task * gm.rows_per_pass);
+    const unsigned nrows = min((unsigned)W::R, rp - gm.warp_off);
+    const unsigned row_g = gm.cta_row0 + task * gm.rows_per_pass + gm.warp_off;
+    const bool row_ok = lane_used && (unsigned)rr < nrows;
+    const bool live = row_ok && ((a.active_mask >> c) & 1ull);
+    const size_t gidx = ((size_t)(row_g + (row_ok ? rr : 0))) * C + c;
+    const unsigned g0 = task * a.n_tiles;
+    // e: the chain's true state at the tile start, in difference coordinates, replicated in the chain's T lanes
+    double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+    if (live) {
+      const double* f = a.filt + gidx * 4;
+      to_diff(f[0], f[1], f[2], f[3], e0, e1, e2, e3);
+    }
+    for (unsigned tile = 0; tile < a.n_tiles; tile++) {
+      const unsigned g = g0 + tile;
+      mbar_wait_warp(&full[g % kWStages], (g / kWStages) & 1);
+      const unsigned char* st = stages + (size_t)(g % kWStages) * W::STAGE_STRIDE;
+      double z1 = 0, z2 = 0, z3 = 0, z4 = 0;
+#pragma unroll 1
+      for (int gi = 0; gi < NG; gi++) {
+        SSBW_GROUP_ADDR(st, gi, grp, kk)
+#pragma unroll
+        for (int j = 0; j < W::U; j++) {
+          const float4 qn = *reinterpret_cast<const float4*>(grp + ((kk ^ j) << 4));
+#pragma unroll
+          for (int f = 0; f < W::FPQ; f++) {
+            const double xn = SSBW_CVT(pickc<C>(qn, f, c));
+            SSBW_ZERO_STEP(xn, z1, z2, z3, z4)
+          }
+        }
+      }
+      // hand-off: lane k keeps the carry after k links as its own start state; after T links e is the next tile's carry
+      double zd0, zd1, zd2, zd3;
+      to_diff(z1, z2, z3, z4, zd0, zd1, zd2, zd3);
+      double dk0 = e0, dk1 = e1, dk2 = e2, dk3 = e3;
+#pragma unroll
+      for (int j = 0; j < T; j++) {
+        const int src = j * Q + q;
+        const double zj0 = __shfl_sync(0xffffffffu, zd0, src), zj1 = __shfl_sync(0xffffffffu, zd1, src);
+        const double zj2 = __shfl_sync(0xffffffffu, zd2, src), zj3 = __shfl_sync(0xffffffffu, zd3, src);
+        const double n0 = fma(SSBW_P(0), e0, fma(SSBW_P(1), e1, fma(SSBW_P(2), e2, fma(SSBW_P(3), e3, zj0))));
+        const double n1 = fma(SSBW_P(4), e0, fma(SSBW_P(5), e1, fma(SSBW_P(6), e2, fma(SSBW_P(7), e3, zj1))));
+        const double n2 = fma(SSBW_P(8), e0, fma(SSBW_P(9), e1, fma(SSBW_P(10), e2, fma(SSBW_P(11), e3, zj2))));
+        const double n3 = fma(SSBW_P(12), e0, fma(SSBW_P(13), e1, fma(SSBW_P(14), e2, fma(SSBW_P(15), e3, zj3))));
+        e0 = n0; e1 = n1; e2 = n2; e3 = n3;
+        if (k == j + 1) { dk0 = n0; dk1 = n1; dk2 = n2; dk3 = n3; }
+      }
+      // publish the start states once the P2 warp has taken the previous tile's
+      if (g >= 1) mbar_wait_warp(dk_free, (g - 1) & 1);
+      reinterpret_cast<double2*>(dk_slot)[lane * 2] = make_double2(dk0, dk1);
+      reinterpret_cast<double2*>(dk_slot)[lane * 2 + 1] = make_double2(dk2, dk3);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dk_full);
+    }
+    // the carry after the last hand-off is the state at the end of the last tile
+    if (row_ok && k == 0 && live) {
+      double c1, c2, c3, c4;
+      from_diff(e0, e1, e2, e3, c1, c2, c3, c4);
+      double* f = a.filt + gidx * 4;
+      const double tiny = 2.2250738585072014e-308;  // libebur128: flush denormal state at the end of a call
+      f[0] = fabs(c1) < tiny ? 0.0 : c1;
+      f[1] = fabs(c2) < tiny ? 0.0 : c2;
+      f[2] = fabs(c3) < tiny ? 0.0 : c3;
+      f[3] = fabs(c4) < tiny ? 0.0 : c4;
+    }
+  }
+#undef SSBW_P
+}
+
+template <class W, int TPF>
+__device__ __forceinline__ void run_p2(const WArgs& a, const CUtensorMap* tmap, unsigned char* stages, uint64_t* full,
+                                       uint64_t* dk_full, uint64_t* dk_free, const double* dk_slot, const PairGeom gm,
+                                       const int lane) {
   constexpr int C = W::C, T = W::T, Q = W::Q, L = W::L, F = W::F;
-  constexpr int NG = L / 16;        // 16-frame groups per segment
+  constexpr int NG = L / 16;
   constexpr int TPW = TPF == 4 ? 11 : (TPF == 2 ? 23 : 1);  // true-peak FIR history length
   static_assert(L % 16 == 0 && TPW <= L, "segments are whole groups; the FIR history of a segment lies inside the previous one");
-  static_assert(NG >= 2 && NG <= 8, "mixmask has one bit per group");
-#define SSBW_P(i) (IS_B ? a.PB[i] : a.PA[i])
-
-  // passes in which this warp owns at least one stream (the last pass may be shorter: the count is monotone)
-  unsigned n_task = 0;
-  for (unsigned p = 0; p < n_pass; p++) {
-    const unsigned rp = min(rows_per_pass, cta_rows - p * rows_per_pass);
-    if (rp > warp_off) n_task++;
-  }
+  const unsigned n_task = count_tasks<W>(gm);
   const unsigned total_tiles = n_task * a.n_tiles;
   if (total_tiles == 0) return;
 
@@ -215,7 +324,7 @@ __device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap
     const unsigned s = g % kWStages;
     mbar_expect_tx(&full[s], W::TX_BYTES);
     tma_load_3d(stages + (size_t)s * W::STAGE_STRIDE, tmap, &full[s], 0,
-                (int)(cta_row0 + p * rows_per_pass + warp_off), (int)(t * W::NL));
+                (int)(gm.cta_row0 + p * gm.rows_per_pass + gm.warp_off), (int)(t * W::NL));
   };
   if (lane == 0) {
     for (unsigned g = 0; g < (unsigned)kWStages && g < total_tiles; g++) issue(g);
@@ -228,148 +337,37 @@ __device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap
   const int c = q - rr * C;
   const int q0 = k * W::NQ;  // first quad of my segment
 
-  // group g of my segment inside a stage: base of its 128-byte line and the swizzle key of its first quad
-#define SSBW_GROUP_ADDR(stage, g, grp, kk)                 \
-  const unsigned char* grp;                                \
-  int kk;                                                  \
-  {                                                        \
-    const int gb_ = q0 + (g) * W::U;                       \
-    const int rl_ = (gb_ >> 3) * W::R + rr;                \
-    grp = (stage) + (rl_ << 7);                            \
-    kk = (gb_ ^ rl_) & 7;                                  \
-  }
-  // hand-off in difference coordinates from P1's end state of a finished tile: e <- Pt e + D z_j, j = 0..T-1; lane k
-  // keeps e after k steps (its segment's start state); after T steps e is the state at the start of the next tile.
-  // BEGIN captures D z and clears P1's state; STEP(j) is one link of the chain (4 shuffled doubles, a 4x4 mat-vec).
-#define SSBW_HO_BEGIN(commit)                                                                                        \
-  double zd0, zd1, zd2, zd3;                                                                                         \
-  to_diff(z1, z2, z3, z4, zd0, zd1, zd2, zd3);                                                                       \
-  z1 = z2 = z3 = z4 = 0.0;                                                                                           \
-  if ((commit) && k == 0) { dk0 = e0; dk1 = e1; dk2 = e2; dk3 = e3; }
-#define SSBW_HO_STEP(j, commit)                                                                                      \
-  {                                                                                                                  \
-    const int src = (j) * Q + q;                                                                                     \
-    const double zj0 = __shfl_sync(0xffffffffu, zd0, src), zj1 = __shfl_sync(0xffffffffu, zd1, src);                 \
-    const double zj2 = __shfl_sync(0xffffffffu, zd2, src), zj3 = __shfl_sync(0xffffffffu, zd3, src);                 \
-    const double n0 = fma(SSBW_P(0), e0, fma(SSBW_P(1), e1, fma(SSBW_P(2), e2, fma(SSBW_P(3), e3, zj0))));          \
-    const double n1 = fma(SSBW_P(4), e0, fma(SSBW_P(5), e1, fma(SSBW_P(6), e2, fma(SSBW_P(7), e3, zj1))));          \
-    const double n2 = fma(SSBW_P(8), e0, fma(SSBW_P(9), e1, fma(SSBW_P(10), e2, fma(SSBW_P(11), e3, zj2))));        \
-    const double n3 = fma(SSBW_P(12), e0, fma(SSBW_P(13), e1, fma(SSBW_P(14), e2, fma(SSBW_P(15), e3, zj3))));      \
-    if (commit) {                                                                                                    \
-      e0 = n0; e1 = n1; e2 = n2; e3 = n3;                                                                            \
-      if (k == (j) + 1) { dk0 = n0; dk1 = n1; dk2 = n2; dk3 = n3; }                                                  \
-    }                                                                                                                \
-  }
-#define SSBW_HANDOFF(commit)                                                        \
-  {                                                                                 \
-    SSBW_HO_BEGIN(commit)                                                           \
-    _Pragma("unroll") for (int j_ = 0; j_ < T; j_++) SSBW_HO_STEP(j_, commit)       \
-  }
-#define SSBW_NOHOOK(j)
-  // one hand-off link after each of the first T quads of the group (the hooks are resolved at compile time)
-#define SSBW_HO_HOOK(j) if ((j) < T) SSBW_HO_STEP(j, has1)
-  // 16 frames of P2 (stage s2, group g2) and 16 frames of P1 (stage s1, group g1), sample by sample
-#define SSBW_FUSED_GROUP(s2, g2, s1, g1, HOOK)                                                 \
-  {                                                                                         \
-    SSBW_GROUP_ADDR(s2, g2, grp2, kk2)                                                      \
-    SSBW_GROUP_ADDR(s1, g1, grp1, kk1)                                                      \
-    double acc = 0.0;                                                                       \
-    _Pragma("unroll") for (int j = 0; j < W::U; j++) {                                      \
-      const float4 qv = *reinterpret_cast<const float4*>(grp2 + ((kk2 ^ j) << 4));          \
-      const float4 qn = *reinterpret_cast<const float4*>(grp1 + ((kk1 ^ j) << 4));          \
-      _Pragma("unroll") for (int f = 0; f < W::FPQ; f++) {                                  \
-        const float xf = pickc<C>(qv, f, c);                                                \
-        if (TPF != 0) sp = fmaxf(sp, fabsf(xf));                                            \
-        const double xd = SSBW_CVT(xf);                                                     \
-        SSBW_FILTER_STEP(xd)                                                                \
-        acc = fma(y_, y_, acc);                                                             \
-        SSBW_TP_STEP(xf)                                                                    \
-        const double xn = SSBW_CVT(pickc<C>(qn, f, c));                                     \
-        SSBW_ZERO_STEP(xn, z1, z2, z3, z4)                                                  \
-      }                                                                                     \
-      HOOK(j)                                                                               \
-    }                                                                                       \
-    if (16 * ((g2) + 1) <= lb) accA += acc; else accB += acc;                               \
-  }
-  // compact (rolled) forms for the pipeline fill and for tiles with a bucket boundary inside a group
-#define SSBW_P1_GROUP(s1, g1)                                                               \
-  {                                                                                         \
-    SSBW_GROUP_ADDR(s1, g1, grp1, kk1)                                                      \
-    _Pragma("unroll 1") for (int j = 0; j < W::U; j++) {                                    \
-      const float4 qn = *reinterpret_cast<const float4*>(grp1 + ((kk1 ^ j) << 4));          \
-      _Pragma("unroll") for (int f = 0; f < W::FPQ; f++) {                                  \
-        const double xn = SSBW_CVT(pickc<C>(qn, f, c));                                     \
-        SSBW_ZERO_STEP(xn, z1, z2, z3, z4)                                                  \
-      }                                                                                     \
-    }                                                                                       \
-  }
-#define SSBW_P2_GROUP(s2, g2)                                                               \
-  {                                                                                         \
-    SSBW_GROUP_ADDR(s2, g2, grp2, kk2)                                                      \
-    int i_ = 16 * (g2);                                                                     \
-    _Pragma("unroll 1") for (int j = 0; j < W::U; j++) {                                    \
-      const float4 qv = *reinterpret_cast<const float4*>(grp2 + ((kk2 ^ j) << 4));          \
-      _Pragma("unroll") for (int f = 0; f < W::FPQ; f++, i_++) {                            \
-        const float xf = pickc<C>(qv, f, c);                                                \
-        if (TPF != 0) sp = fmaxf(sp, fabsf(xf));                                            \
-        const double xd = SSBW_CVT(xf);                                                     \
-        SSBW_FILTER_STEP(xd)                                                                \
-        if (i_ < lb) accA = fma(y_, y_, accA); else accB = fma(y_, y_, accB);               \
-        SSBW_TP_STEP(xf)                                                                    \
-      }                                                                                     \
-    }                                                                                       \
-  }
-
   for (unsigned task = 0; task < n_task; task++) {
-    const unsigned rp = min(rows_per_pass, cta_rows - task * rows_per_pass);
-    const unsigned nrows = min((unsigned)W::R, rp - warp_off);
-    const unsigned row_g = cta_row0 + task * rows_per_pass + warp_off;  // first stream of this warp's box
+    const unsigned rp = min(gm.rows_per_pass, gm.cta_rows - task * gm.rows_per_pass);
+    const unsigned nrows = min((unsigned)W::R, rp - gm.warp_off);
+    const unsigned row_g = gm.cta_row0 + task * gm.rows_per_pass + gm.warp_off;  // first stream of this pair's box
     const bool row_ok = lane_used && (unsigned)rr < nrows;
     const bool live = row_ok && ((a.active_mask >> c) & 1ull);
     const bool owner = row_ok && k == 0;
     const size_t gidx = ((size_t)(row_g + (row_ok ? rr : 0))) * C + c;
     const unsigned g0 = task * a.n_tiles;
-#define SSBW_STAGE(tile) (stages + (size_t)((g0 + (tile)) % kWStages) * W::STAGE_STRIDE)
-#define SSBW_WAIT(tile) mbar_wait_warp(&full[(g0 + (tile)) % kWStages], ((g0 + (tile)) / kWStages) & 1)
 
-    // e: the chain's true state at a tile start, in difference coordinates, replicated in the chain's T lanes;
-    // dk: this lane's own start state for the tile P2 is about to run
-    double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-    if (live) {
-      const double* f = a.filt + gidx * 4;
-      to_diff(f[0], f[1], f[2], f[3], e0, e1, e2, e3);
-    }
-    double dk0 = 0, dk1 = 0, dk2 = 0, dk3 = 0;
-    double z1 = 0, z2 = 0, z3 = 0, z4 = 0;   // P1: zero-state recursion over my segment of its current tile
-    double v1 = 0, v2 = 0, v3 = 0, v4 = 0;   // P2: the filter state
-    double acc_cur = 0.0;                    // owner lane: running sum (already times b0^2) of the bucket in progress
+    double acc_cur = 0.0;  // owner lane: running sum (already times b0^2) of the bucket in progress
     unsigned slot = a.slot0;
     if (owner && live && a.pos0 > 0) acc_cur = a.bucket[gidx * kNB + slot];
     float sp = 0.f, tp = 0.f;
-    float hist[TPW];   // the TPW samples before P2's next tile, hist[t] = x[n-1-t] (meaningful in the k == 0 lanes)
+    float hist[TPW];   // the TPW samples before the next tile, hist[t] = x[n-1-t] (meaningful in the k == 0 lanes)
 #pragma unroll
     for (int t = 0; t < TPW; t++) hist[t] = (TPF >= 2 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
-    unsigned pos_tile = a.pos0;   // position of P2's current tile start inside the bucket in progress
-
-    // ---- pipeline fill: P1 over the whole first tile, its hand-off, P1's first group of the second tile ----
-    SSBW_WAIT(0);
-    {
-      const unsigned char* st = SSBW_STAGE(0);
-#pragma unroll 1
-      for (int g = 0; g < NG; g++) SSBW_P1_GROUP(st, g)
-    }
-    SSBW_HANDOFF(true)
-    if (a.n_tiles > 1) {
-      SSBW_WAIT(1);
-      const unsigned char* st = SSBW_STAGE(1);
-      SSBW_P1_GROUP(st, 0)
-    }
+    unsigned pos_tile = a.pos0;   // position of the tile start inside the bucket in progress
 
     for (unsigned tile = 0; tile < a.n_tiles; tile++) {
-      const bool has1 = tile + 1 < a.n_tiles, has2 = tile + 2 < a.n_tiles;
-      const unsigned char* st0 = SSBW_STAGE(tile);
-      // ---- P2 starts the tile from the state the hand-off left in dk ----
-      from_diff(dk0, dk1, dk2, dk3, v1, v2, v3, v4);
+      const unsigned g = g0 + tile;
+      const unsigned char* st0 = stages + (size_t)(g % kWStages) * W::STAGE_STRIDE;
+      // ---- start states from the P1 warp (it has seen the tile land; the second wait makes the TMA writes visible here) ----
+      mbar_wait_warp(dk_full, g & 1);
+      const double2 da = reinterpret_cast<const double2*>(dk_slot)[lane * 2];
+      const double2 db = reinterpret_cast<const double2*>(dk_slot)[lane * 2 + 1];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dk_free);
+      mbar_wait_warp(&full[g % kWStages], (g / kWStages) & 1);
+      double v1, v2, v3, v4;
+      from_diff(da.x, da.y, db.x, db.y, v1, v2, v3, v4);
       const unsigned to_boundary = a.s100 - pos_tile;  // frames of this tile before the bucket boundary (>= F: none inside)
       int lb = (int)to_boundary - k * L;               // my samples [0, lb) belong to the bucket in progress
       lb = lb < 0 ? 0 : (lb > L ? L : lb);
@@ -388,43 +386,54 @@ __device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap
         }
       }
       if (!mixed) {
-        // ---- the steady state.  Without a next tile P1 reruns over this one and its result is dropped. ----
-        const unsigned char* s1 = has1 ? SSBW_STAGE(tile + 1) : st0;
 #pragma unroll 1
-        for (int g = 0; g < NG - 1; g++) SSBW_FUSED_GROUP(st0, g, s1, g + 1, SSBW_NOHOOK)
-        if (has2) SSBW_WAIT(tile + 2);
-        const unsigned char* s2n = has2 ? SSBW_STAGE(tile + 2) : st0;
-        // P1 has finished tile + 1: its hand-off is threaded through P2's last group, one link per quad
-        SSBW_HO_BEGIN(has1)
-        SSBW_FUSED_GROUP(st0, NG - 1, s2n, 0, SSBW_HO_HOOK)
+        for (int gi = 0; gi < NG; gi++) {
+          SSBW_GROUP_ADDR(st0, gi, grp, kk)
+          double acc = 0.0;
 #pragma unroll
-        for (int j_ = W::U; j_ < T; j_++) SSBW_HO_STEP(j_, has1)   // mono: 4 quads per group, up to 5 links
+          for (int j = 0; j < W::U; j++) {
+            const float4 qv = *reinterpret_cast<const float4*>(grp + ((kk ^ j) << 4));
+#pragma unroll
+            for (int f = 0; f < W::FPQ; f++) {
+              const float xf = pickc<C>(qv, f, c);
+              if (TPF != 0) sp = fmaxf(sp, fabsf(xf));
+              const double xd = SSBW_CVT(xf);
+              SSBW_FILTER_STEP(xd)
+              acc = fma(y_, y_, acc);
+              SSBW_TP_STEP(xf)
+            }
+          }
+          if (16 * (gi + 1) <= lb) accA += acc; else accB += acc;
+        }
       } else {
+        // a bucket boundary strictly inside some lane's group (rates whose 100 ms is not whole tiles): per-sample test
+        int i_ = 0;
 #pragma unroll 1
-        for (int g = 0; g < NG; g++) {
-          SSBW_P2_GROUP(st0, g)
-          if (has1 && g < NG - 1) {
-            const unsigned char* s1 = SSBW_STAGE(tile + 1);
-            SSBW_P1_GROUP(s1, g + 1)
+        for (int gi = 0; gi < NG; gi++) {
+          SSBW_GROUP_ADDR(st0, gi, grp, kk)
+#pragma unroll 1
+          for (int j = 0; j < W::U; j++) {
+            const float4 qv = *reinterpret_cast<const float4*>(grp + ((kk ^ j) << 4));
+#pragma unroll
+            for (int f = 0; f < W::FPQ; f++, i_++) {
+              const float xf = pickc<C>(qv, f, c);
+              if (TPF != 0) sp = fmaxf(sp, fabsf(xf));
+              const double xd = SSBW_CVT(xf);
+              SSBW_FILTER_STEP(xd)
+              if (i_ < lb) accA = fma(y_, y_, accA); else accB = fma(y_, y_, accB);
+              SSBW_TP_STEP(xf)
+            }
           }
         }
-        SSBW_HANDOFF(has1)
-        if (has2) {
-          SSBW_WAIT(tile + 2);
-          const unsigned char* s2n = SSBW_STAGE(tile + 2);
-          SSBW_P1_GROUP(s2n, 0)
-        }
       }
-      if (!has2) { z1 = z2 = z3 = z4 = 0.0; }   // nothing real ran in P1's last group
-
-      // ---- P2 has finished the tile: FIR history, stage back to the TMA ring (the tile three ahead, possibly the next
-      //      pass's), bucket sums (fixed-order reduction over the segments, times b0^2) ----
+      // ---- the tile is done: FIR history, stage back to the TMA ring (the tile three ahead, possibly the next pass's),
+      //      bucket sums (fixed-order reduction over the segments, times b0^2) ----
       if (TPF >= 2) {
 #pragma unroll
         for (int t = 0; t < TPW; t++) hist[t] = __shfl_sync(0xffffffffu, w2[t].x, (T - 1) * Q + q);
       }
       __syncwarp();
-      if (lane == 0 && g0 + tile + kWStages < total_tiles) issue(g0 + tile + kWStages);
+      if (lane == 0 && g + kWStages < total_tiles) issue(g + kWStages);
       const double sA = seg_sum<W>(accA, q);
       if (to_boundary <= (unsigned)F) {
         const double sB = seg_sum<W>(accB, q);
@@ -441,23 +450,11 @@ __device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap
       if (pos_tile >= a.s100) pos_tile -= a.s100;
     }
 
-    // ---------------- end of this warp's streams for this pass: state, bucket in progress, peaks ----------------
+    // ---------------- end of this pair's streams for this pass: bucket in progress, peaks ----------------
     sp = seg_max<W>(sp, q);
     tp = seg_max<W>(tp, q);
     if (owner) {
-      if (live) {
-        a.bucket[gidx * kNB + slot] = acc_cur;
-        double c1, c2, c3, c4;
-        from_diff(e0, e1, e2, e3, c1, c2, c3, c4);   // the carry after the last hand-off: state at the end of the last tile
-        double* f = a.filt + gidx * 4;
-        const double tiny = 2.2250738585072014e-308;  // libebur128: flush denormal state at the end of a call
-        f[0] = fabs(c1) < tiny ? 0.0 : c1;
-        f[1] = fabs(c2) < tiny ? 0.0 : c2;
-        f[2] = fabs(c3) < tiny ? 0.0 : c3;
-        f[3] = fabs(c4) < tiny ? 0.0 : c4;
-      } else {
-        a.bucket[gidx * kNB + slot] = 0.0;
-      }
+      a.bucket[gidx * kNB + slot] = live ? acc_cur : 0.0;
       if (TPF != 0) a.speak[gidx] = fmaxf(a.speak[gidx], sp);
       if (TPF >= 2) {
         a.tpeak[gidx] = fmaxf(a.tpeak[gidx], tp);
@@ -465,32 +462,23 @@ __device__ __forceinline__ void run_warp(const WArgs& a, const CUtensorMap* tmap
         for (int t = 0; t < TPW; t++) a.tphist[gidx * kTpHist + t] = hist[t];
       }
     }
-#undef SSBW_STAGE
-#undef SSBW_WAIT
   }
-#undef SSBW_GROUP_ADDR
-#undef SSBW_HANDOFF
-#undef SSBW_HO_BEGIN
-#undef SSBW_HO_STEP
-#undef SSBW_NOHOOK
-#undef SSBW_HO_HOOK
-#undef SSBW_FUSED_GROUP
-#undef SSBW_P1_GROUP
-#undef SSBW_P2_GROUP
-#undef SSBW_P
 }
+#undef SSBW_GROUP_ADDR
 
 // MIXED: type A = (T 4, L 80), type B = (T 5, L 64), 320-frame tiles, 28 stereo streams per pass;
-// !MIXED: every warp (T 4, L 64), 256-frame tiles, 32 stereo streams per pass.
+// !MIXED: every set (T 4, L 64), 256-frame tiles, 32 stereo streams per pass.
 template <int C, bool MIXED>
 struct WCfg {
   using A = WType<C, 4, 8 / C, MIXED ? 80 : 64>;
   using B = WType<C, MIXED ? 5 : 4, (MIXED ? 6 : 8) / C, 64>;
-  static_assert(A::F == B::F, "both warp types walk the same tiles");
+  static_assert(A::F == B::F, "both set types walk the same tiles");
   static constexpr int F = A::F;
   static constexpr int CAP = 4 * A::R + 4 * B::R;  // streams per CTA pass
-  static constexpr size_t SMEM = (size_t)4 * kWStages * (A::STAGE_STRIDE + B::STAGE_STRIDE) +
-                                 (size_t)kWWarps * kWStages * sizeof(uint64_t) + 1024;
+  static constexpr size_t STAGES = (size_t)4 * kWStages * (A::STAGE_STRIDE + B::STAGE_STRIDE);
+  static constexpr size_t DK = (size_t)kWPairs * 32 * 4 * sizeof(double);        // one start-state slot per pair
+  static constexpr size_t BARS = (size_t)kWPairs * kWBars * sizeof(uint64_t);
+  static constexpr size_t SMEM = STAGES + DK + BARS + 1024;
 };
 
 template <int C, int TPF, bool MIXED>
@@ -503,9 +491,12 @@ k_loudness_wtile(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
   using WB = typename Cfg::B;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)4 * kWStages * (WA::STAGE_STRIDE + WB::STAGE_STRIDE));
+  double* dk_all = reinterpret_cast<double*>(smem + Cfg::STAGES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES + Cfg::DK);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp & (kWPairs - 1);     // warps 0..7: the P2 warps, 8..15: the P1 warps of the same pairs
+  const bool is_p1 = warp >= kWPairs;        // pair p and p + 4, P1 and P2: warps p, p+4, p+8, p+12 share sub-partition p % 4
   const unsigned n_ctas = gridDim.x;
   const unsigned row0 = (unsigned)(((unsigned long long)blockIdx.x * a.n_streams) / n_ctas);
   const unsigned row1 = (unsigned)(((unsigned long long)(blockIdx.x + 1) * a.n_streams) / n_ctas);
@@ -513,21 +504,30 @@ k_loudness_wtile(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
   const unsigned n_pass = (cta_rows + Cfg::CAP - 1) / Cfg::CAP;
   const unsigned rows_per_pass = n_pass ? (cta_rows + n_pass - 1) / n_pass : 0;
 
-  uint64_t* full = bars + warp * kWStages;
-  if (lane == 0) {
-    for (int s = 0; s < kWStages; s++) mbar_init(&full[s], 1);
+  uint64_t* full = bars + pair * kWBars;    // [0..2] TMA full, [3] dk_full, [4] dk_free
+  if (!is_p1 && lane == 0) {
+    for (int s = 0; s < kWBars; s++) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
-  __syncwarp();
+  __syncthreads();
 
   if (cta_rows) {
-    if (warp < 4) {
-      unsigned char* stages = smem + (size_t)warp * kWStages * WA::STAGE_STRIDE;
-      run_warp<WA, false, TPF>(a, &tmapA, stages, full, row0, cta_rows, rows_per_pass, n_pass, (unsigned)warp * WA::R, lane);
+    PairGeom gm;
+    gm.cta_row0 = row0;
+    gm.cta_rows = cta_rows;
+    gm.rows_per_pass = rows_per_pass;
+    gm.n_pass = n_pass;
+    double* dk_slot = dk_all + (size_t)pair * 32 * 4;
+    if (pair < 4) {
+      unsigned char* stages = smem + (size_t)pair * kWStages * WA::STAGE_STRIDE;
+      gm.warp_off = (unsigned)pair * WA::R;
+      if (is_p1) run_p1<WA, false>(a, stages, full, full + 3, full + 4, dk_slot, gm, lane);
+      else run_p2<WA, TPF>(a, &tmapA, stages, full, full + 3, full + 4, dk_slot, gm, lane);
     } else {
-      unsigned char* stages = smem + (size_t)4 * kWStages * WA::STAGE_STRIDE + (size_t)(warp - 4) * kWStages * WB::STAGE_STRIDE;
-      run_warp<WB, true, TPF>(a, &tmapB, stages, full, row0, cta_rows, rows_per_pass, n_pass,
-                              4u * WA::R + (unsigned)(warp - 4) * WB::R, lane);
+      unsigned char* stages = smem + (size_t)4 * kWStages * WA::STAGE_STRIDE + (size_t)(pair - 4) * kWStages * WB::STAGE_STRIDE;
+      gm.warp_off = 4u * WA::R + (unsigned)(pair - 4) * WB::R;
+      if (is_p1) run_p1<WB, true>(a, stages, full, full + 3, full + 4, dk_slot, gm, lane);
+      else run_p2<WB, TPF>(a, &tmapB, stages, full, full + 3, full + 4, dk_slot, gm, lane);
     }
   }
   if (a.fused_results) {

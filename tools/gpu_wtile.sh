@@ -1,9 +1,13 @@
 #!/bin/bash
-# k_loudness_wtile on the GPU: parity tests, A/B timing, ncu captures (filter only, and with the fused epilogue)
+# k_loudness_wtile on the GPU: parity tests, A/B timing, ncu capture (filter only)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_wtile.py tests/test_gpu_ebu.py -m gpu -q -s -x > gpurun_out/wt_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/wt_pytest.log
 timeout 300 python tools/time_wtile.py > gpurun_out/wt_time.log 2>&1
+for v in 0 2; do
+  echo "SSB_RESULTS_V=$v" >> gpurun_out/wt_time.log
+  SSB_RESULTS_V=$v FORCES=0 MODES=loudness timeout 120 python tools/time_wtile.py >> gpurun_out/wt_time.log 2>&1
+done
 NOFUSE=1 FORCE=5 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_loudness_wtile -s 3 -c 1 \
   -o gpurun_out/prof_wtile -f python tools/prof_cfg2.py > gpurun_out/prof_wtile.log 2>&1
 tail -n 12 gpurun_out/wt_pytest.log; cat gpurun_out/wt_time.log

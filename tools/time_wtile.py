@@ -12,8 +12,12 @@ torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
 xs = [make_input_device_chunked(torch, n, FRAMES, 1234 + i, dev, chunk=2048, channels=CH) for i in range(2)]
 peak = 6514.8
+MODES = os.environ.get("MODES", "loudness,all").split(",")
+FORCES = [int(v) for v in os.environ.get("FORCES", "3,5,6,0").split(",")]
 for mode_name, mode in (("loudness", S.MODE_LOUDNESS), ("all", S.MODE_ALL)):
-    for fk in (3, 5, 6, 0):
+    if mode_name not in MODES:
+        continue
+    for fk in FORCES:
         an = S.BatchAnalyzer(n, CH, RATE, mode, device=0)
         an.force_kernel(fk)
         res = torch.empty((n, an.stride), dtype=torch.float64, device=dev)
