@@ -106,8 +106,14 @@ def test_bench_reference_arm_contract():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
-    assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    e2e = line["e2e"]
+    assert e2e["value"] == line["value"] and e2e["unit"] == "samples/s" and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
     assert "cfg2" in line["config"]["workload"] and line["vs_baseline"] is None and line["gpu_launches"] == 0
+    # Mode::all() (what the reference's Analyzer always builds, analyzer.rs:36,51,171) is reported beside the loudness modes
+    assert line["value_all"] > 0 and line["cpu_baseline_all"]["kind"] == "port" and line["e2e_all"]["value"] == line["value_all"]
+    # the config object is the one the GPU arm prints for the same --gpus (the driver compares them)
+    import bench
+    assert line["config"] == bench.bench_config(1)
 
 
 def test_header_is_plain_c_and_links_from_c(ssb):
