@@ -51,6 +51,7 @@ enum {
   SSB_ERR_CAPACITY = 11,             /* caller's output buffer too small; required size written to *n_out */
   SSB_ERR_UNALIGNED_QUERY = 12,      /* momentary/short-term query off the 100 ms grid on a handle built without SSB_FLAG_RING */
   SSB_ERR_NO_DEVICE = 13,
+  SSB_ERR_BUSY = 14,                 /* a capture-ring snapshot kept colliding with the producer; nothing was wrong, try again */
   SSB_ERR_CUDA = 100                 /* 100 + cudaError_t */
 };
 
@@ -175,7 +176,9 @@ enum { SSB_FFT_MONO = 0, SSB_FFT_MID_SIDE = 1 };
  * in[w][n][2] interleaved stereo; mid/side are formed as get_mid_and_side_samples does
  * (audio_player.rs:400-419) and both spectra are produced.  d_db_out[w][planes][n_bins] f32 receives
  * scale_to_dbfs (analyzer.rs:11-27) BEFORE the f64 tilt (planes = 1 or 2); add ssb_fft_axis's tilt to
- * get the reference's y.  d_status[w] (optional) receives per-window SSB_ERR_FFT_* codes. */
+ * get the reference's y.  d_status[w] (optional) receives per-window SSB_ERR_FFT_* codes. 
+ * ALIGNMENT: d_in must be 16-byte aligned (windows are read with vector loads); a misaligned pointer returns
+ * SSB_ERR_INVALID_ARG instead of faulting. */
 int32_t ssb_fft_batch_device(ssb_analyzer* h, const float* d_in, int32_t layout, size_t n,
                              size_t n_windows, float* d_db_out, int32_t* d_status);
 
@@ -271,8 +274,14 @@ int32_t ssb_waveform_device(ssb_analyzer* h, const float* d_samples, size_t len,
 /* get_mid_and_side_samples (audio_player.rs:400-419): HOST in, HOST out; *frames = len/2 */
 int32_t ssb_mid_side(ssb_analyzer* h, const float* interleaved, size_t len, float* mid, float* side,
                      size_t* frames);
+/* device form.  ALIGNMENT: d_interleaved must be 8-byte aligned (SSB_ERR_INVALID_ARG otherwise). */
 int32_t ssb_mid_side_device(ssb_analyzer* h, const float* d_interleaved, size_t len, float* d_mid,
                             float* d_side);
+
+/* The two get_fft statuses of the last ssb_process_tick / ssb_mic_tick separately: mid_side[0] for the mid spectrum,
+ * mid_side[1] for the side spectrum (the reference handles the two results independently, tui.rs:1505-1523; the tick
+ * calls' own fft_status is the first non-zero of the two). */
+int32_t ssb_tick_fft_status(const ssb_analyzer* h, int32_t mid_side[2]);
 
 /* ---- kernel timing (bench.py's roofline leg) ------------------------------------------------ */
 /* when enabled, every K-weighting (filter) launch is bracketed by CUDA events on the handle's stream */

@@ -31,7 +31,7 @@ OK = 0
 ERR_NAMES = {
     1: "NoMem", 2: "InvalidMode", 3: "InvalidChannelIndex", 4: "TooFewSamples", 5: "NaNValuesNotSupported",
     6: "InfinityValuesNotSupported", 7: "SamplesLengthNotAPowerOfTwo", 8: "InvalidFrequencyLimit",
-    9: "ScalingError", 10: "InvalidArgument", 11: "Capacity", 12: "UnalignedQuery", 13: "NoDevice",
+    9: "ScalingError", 10: "InvalidArgument", 11: "Capacity", 12: "UnalignedQuery", 13: "NoDevice", 14: "Busy",
 }
 
 
@@ -54,7 +54,7 @@ SYMBOLS = [
     "ssb_calculate_integrated_lufs", "ssb_get_fft", "ssb_fft_bins", "ssb_fft_axis", "ssb_fft_batch_device",
     "ssb_process_tick", "ssb_preanalyze_file", "ssb_get_waveform", "ssb_waveform_device", "ssb_mid_side", "ssb_mid_side_device", "ssb_filter_coeffs",
     "ssb_histograms", "ssb_profile_enable", "ssb_profile_read", "ssb_debug_force_generic", "ssb_gather_create", "ssb_gather_open", "ssb_gather_select", "ssb_gather_rows", "ssb_gather_epoch", "ssb_gather_wait", "ssb_gather_destroy",
-    "ssb_true_peak_factor", "ssb_debug_force_true_peak_factor", "ssb_debug_histogram_index",
+    "ssb_tick_fft_status", "ssb_true_peak_factor", "ssb_debug_force_true_peak_factor", "ssb_debug_histogram_index",
     "ssb_pcm_bytes_per_sample", "ssb_pcm_to_f32", "ssb_pcm_to_f32_device", "ssb_add_frames_pcm", "ssb_add_frames_pcm_device",
     "ssb_capture_ring_create", "ssb_capture_ring_destroy", "ssb_capture_ring_capacity", "ssb_capture_ring_written",
     "ssb_capture_ring_push", "ssb_capture_ring_to_vec", "ssb_mic_tick",
@@ -113,6 +113,7 @@ def lib():
         "ssb_gather_epoch": (C.c_uint64, [vp]),
         "ssb_gather_wait": (C.c_int32, [vp]),
         "ssb_gather_destroy": (C.c_int32, [vp]),
+        "ssb_tick_fft_status": (C.c_int32, [vp, vp]),
         "ssb_true_peak_factor": (C.c_int32, [vp]),
         "ssb_debug_force_true_peak_factor": (C.c_int32, [vp, C.c_int32]),
         "ssb_calculate_integrated_lufs": (C.c_int32, [vp, C.c_uint32, f32p, C.c_size_t, C.POINTER(C.c_double), i32p]),

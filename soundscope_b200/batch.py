@@ -228,6 +228,7 @@ class BatchAnalyzer:
         """x: [W, n] (mono) or [W, n, 2] (stereo -> mid, side) f32 CUDA tensor -> dB [W, planes, n_bins] f32."""
         import torch
         assert x.is_cuda and x.is_contiguous()
+        assert x.data_ptr() % 16 == 0, "fft_batch_device: the input view must start on a 16-byte boundary"
         layout = FFT_MID_SIDE if x.dim() == 3 else FFT_MONO
         w, n = x.shape[0], x.shape[1]
         _, nb = self.fft_bins(n)
@@ -253,6 +254,7 @@ class BatchAnalyzer:
     def mid_side_device(self, x):
         import torch
         assert x.is_cuda and x.is_contiguous()
+        assert x.data_ptr() % 8 == 0, "mid_side_device: the input view must start on an 8-byte boundary"
         frames = x.numel() // 2
         mid = torch.empty(frames, dtype=torch.float32, device=x.device)
         side = torch.empty(frames, dtype=torch.float32, device=x.device)

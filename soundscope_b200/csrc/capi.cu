@@ -746,6 +746,10 @@ int32_t ssb_fft_batch_device(ssb_analyzer* h, const float* d_in, int32_t layout,
                              float* d_db_out, int32_t* d_status) {
   if (!h || !d_in || !d_db_out) return SSB_ERR_INVALID_ARG;
   if (layout != SSB_FFT_MONO && layout != SSB_FFT_MID_SIDE) return fail(h, SSB_ERR_INVALID_ARG, "bad layout");
+  // the kernels read the windows with 8- and 16-byte vector loads: a misaligned device pointer (an odd-offset view of a
+  // larger buffer) would fault and poison the context, so it is refused here
+  if (((uintptr_t)d_in & 15) != 0 || ((uintptr_t)d_db_out & 3) != 0)
+    return fail(h, SSB_ERR_INVALID_ARG, "ssb_fft_batch_device: d_in must be 16-byte aligned (got %p)", (const void*)d_in);
   int32_t rc = fft_shape_check(n, h->rate);
   if (rc) return fail(h, rc, "get_fft: invalid length %zu / rate %u", n, h->rate);
   DeviceGuard g(h->device);
@@ -814,6 +818,7 @@ int32_t ssb_process_tick(ssb_analyzer* h, const float* tail, size_t n_fft, size_
   if (lufs_samples > 2 * n_fft) return fail(h, SSB_ERR_INVALID_ARG, "lufs_samples exceeds the tail");
   *n_points = 0;
   *fft_status = fft_shape_check(n_fft, h->rate);
+  h->tick_fft_status[0] = h->tick_fft_status[1] = *fft_status;
   *lufs_status = (lufs_samples % 2 != 0) ? SSB_ERR_NOMEM : SSB_OK;  // add_frames_f32: ragged -> Error::NoMem
   DeviceGuard g(h->device);
   FftPlan* plan = nullptr;
@@ -858,6 +863,8 @@ int32_t ssb_process_tick(ssb_analyzer* h, const float* tail, size_t n_fft, size_
     const float* db = static_cast<const float*>(h->h_scratch);
     const int32_t* st = reinterpret_cast<const int32_t*>(db + 2 * nb);
     *fft_status = st[0] ? st[0] : st[1];
+    h->tick_fft_status[0] = st[0];   // the reference handles the two get_fft results independently (tui.rs:1505-1523)
+    h->tick_fft_status[1] = st[1];
     const auto& axes = fft_axis_cached(h, n_fft, h->rate);
     const std::vector<double>& ax = axes.first;
     const std::vector<double>& tilt = axes.second;
@@ -935,6 +942,8 @@ int32_t ssb_mid_side_device(ssb_analyzer* h, const float* d_interleaved, size_t 
   const size_t frames = len / 2;
   if (!frames) return SSB_OK;
   if (!d_interleaved || !d_mid || !d_side) return SSB_ERR_INVALID_ARG;
+  if (((uintptr_t)d_interleaved & 7) != 0)   // read as (l, r) pairs with 8-byte loads
+    return fail(h, SSB_ERR_INVALID_ARG, "ssb_mid_side_device: d_interleaved must be 8-byte aligned (got %p)", (const void*)d_interleaved);
   DeviceGuard g(h->device);
   CK(launch_mid_side(d_interleaved, frames, d_mid, d_side, h->stream, &h->launches));
   return SSB_OK;
@@ -959,6 +968,13 @@ int32_t ssb_mid_side(ssb_analyzer* h, const float* interleaved, size_t len, floa
   CK(cudaMemcpyAsync(mid, d_mid, half, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(side, d_side, half, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return SSB_OK;
+}
+
+int32_t ssb_tick_fft_status(const ssb_analyzer* h, int32_t mid_side[2]) {
+  if (!h || !mid_side) return SSB_ERR_INVALID_ARG;
+  mid_side[0] = h->tick_fft_status[0];
+  mid_side[1] = h->tick_fft_status[1];
   return SSB_OK;
 }
 

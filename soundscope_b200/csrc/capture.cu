@@ -265,7 +265,15 @@ namespace {
 // Bring the device mirror up to the producer's published position: copies only the physical spans written since
 // the last call.  Returns the snapshot position W (to_vec() is then the cap values ending at W).
 int32_t ring_sync_mirror(ssb_analyzer* h, ssb_capture_ring* r, uint64_t* w_out) {
-  for (int attempt = 0; attempt < 4; attempt++) {
+  // The reference's to_vec runs under the ring's mutex and cannot fail; this one is lock-free, so a copy that a push
+  // overlapped is retried.  Each attempt first waits (bounded) for the push in flight to publish: with a live audio
+  // callback (a few hundred microseconds of stores every ~10 ms) the second attempt practically always succeeds.
+  for (int attempt = 0; attempt < 64; attempt++) {
+    for (int spin = 0; spin < (1 << 16) && r->claimed.load(std::memory_order_acquire) != r->written.load(std::memory_order_acquire); spin++) {
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
     const uint64_t w = r->written.load(std::memory_order_acquire);
     uint64_t from = r->mirrored;
     if (w - from >= r->cap) from = w - r->cap;  // everything older has been overwritten
@@ -452,7 +460,15 @@ int32_t ssb_capture_ring_push(ssb_capture_ring* r, const float* data, size_t n, 
 
 int32_t ssb_capture_ring_to_vec(ssb_capture_ring* r, float* out, size_t cap) {
   if (!r || !out || cap < r->cap) return SSB_ERR_INVALID_ARG;
-  for (int attempt = 0; attempt < 4; attempt++) {
+  // The reference's to_vec runs under the ring's mutex and cannot fail; this one is lock-free, so a copy that a push
+  // overlapped is retried.  Each attempt first waits (bounded) for the push in flight to publish: with a live audio
+  // callback (a few hundred microseconds of stores every ~10 ms) the second attempt practically always succeeds.
+  for (int attempt = 0; attempt < 64; attempt++) {
+    for (int spin = 0; spin < (1 << 16) && r->claimed.load(std::memory_order_acquire) != r->written.load(std::memory_order_acquire); spin++) {
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
     const uint64_t w = r->written.load(std::memory_order_acquire);
     const size_t oldest = (size_t)(w % r->cap);
     memcpy(out, r->h_ring + oldest, (r->cap - oldest) * sizeof(float));
@@ -460,7 +476,7 @@ int32_t ssb_capture_ring_to_vec(ssb_capture_ring* r, float* out, size_t cap) {
     std::atomic_thread_fence(std::memory_order_seq_cst);
     if (r->claimed.load(std::memory_order_acquire) == w) return SSB_OK;  // no push started during the copy
   }
-  return SSB_ERR_INVALID_ARG;
+  return SSB_ERR_BUSY;
 }
 
 int32_t ssb_mic_tick(ssb_analyzer* h, ssb_capture_ring* ring, size_t n_fft, size_t lufs_samples, double waveform_window,
@@ -480,6 +496,7 @@ int32_t ssb_mic_tick(ssb_analyzer* h, ssb_capture_ring* ring, size_t n_fft, size
     return fail(h, SSB_ERR_INVALID_ARG, "mic_tick: the reference's slices [15*rate - n_fft, 15*rate) / "
                 "[30*rate - lufs_samples, 30*rate) do not fit a ring of %zu values at rate %zu", ring->cap, rate);
   *fft_status = fft_shape_check(n_fft, h->rate);
+  h->tick_fft_status[0] = h->tick_fft_status[1] = *fft_status;
   *lufs_status = (lufs_samples % h->channels != 0) ? SSB_ERR_NOMEM : SSB_OK;  // add_frames_f32: ragged -> NoMem
   DeviceGuard g(h->device);
   FftPlan* plan = nullptr;
@@ -567,6 +584,8 @@ int32_t ssb_mic_tick(ssb_analyzer* h, ssb_capture_ring* ring, size_t n_fft, size
     const float* db = reinterpret_cast<const float*>(static_cast<const char*>(h->h_scratch) + wave_bytes);
     const int32_t* st = reinterpret_cast<const int32_t*>(db + 2 * nb);
     *fft_status = st[0] ? st[0] : st[1];
+    h->tick_fft_status[0] = st[0];   // the reference handles the two get_fft results independently (tui.rs:1505-1523)
+    h->tick_fft_status[1] = st[1];
     const auto& axes = fft_axis_cached(h, n_fft, h->rate);
     const std::vector<double>& ax = axes.first;
     const std::vector<double>& tilt = axes.second;

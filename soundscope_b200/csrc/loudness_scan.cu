@@ -317,6 +317,10 @@ bool scan_path_usable(const LoudParams& p, const LoudState& st, size_t frames) {
   if (st.n_streams > 64) return false;          // many streams: the batch kernels win
   if (p.s100 < (unsigned)kScanLS) return false;
   if (frames < 512) return false;               // short calls: the serial kernel's latency is lower
+  // A sweep covers 256 / C segments of kScanLS frames whose lanes write the ring concurrently: if the ring is shorter
+  // than a sweep (rates below ~2.7 kHz stereo / 5.4 kHz mono) two segments of one sweep would land on the same slot in
+  // an undefined order — those handles take the serial kernel
+  if (st.ring && st.ring_frames < (size_t)(256 / p.channels) * kScanLS) return false;
   return true;
 }
 

@@ -72,6 +72,7 @@ struct WType {
   static constexpr int NQ = L * C / 4;      // 16-byte quads per segment
   static constexpr int FPQ = 4 / C;         // frames per quad
   static constexpr int U = 16 / FPQ;        // quads per unrolled group (16 frames)
+  static constexpr int SHQ = 4 / FPQ;       // quads of lookahead: the recursions consume samples four ahead
   static constexpr int NL = F * C / 32;     // 128-byte lines per stream per tile
   static constexpr unsigned TX_BYTES = R * NL * 128;
   static constexpr unsigned STAGE_STRIDE = (TX_BYTES + 1023u) / 1024u * 1024u;  // SWIZZLE_128B: 1 KB aligned stages
@@ -115,25 +116,50 @@ __device__ __forceinline__ void from_diff(double d0, double d1, double d2, doubl
 
 #define SSBW_CVT(x) ((double)(x))
 
-// One filter sample: DF-II recursion (newest state last: short dependent chain) + scaled output tap.
-#define SSBW_FILTER_STEP(x)                      \
-  double t_ = fma(a.na[4], v4, (x));             \
-  t_ = fma(a.na[3], v3, t_);                     \
-  t_ = fma(a.na[2], v2, t_);                     \
-  const double v0_ = fma(a.na[1], v1, t_);       \
-  double y_ = fma(a.cy[4], v4, (x));             \
-  y_ = fma(a.cy[3], v3, y_);                     \
-  y_ = fma(a.cy[2], v2, y_);                     \
-  y_ = fma(a.cy[1], v1, y_);                     \
-  v4 = v3; v3 = v2; v2 = v1; v1 = v0_;
-
-#define SSBW_ZERO_STEP(x, z1, z2, z3, z4)        \
-  {                                              \
-    double tz_ = fma(a.na[4], z4, (x));          \
-    tz_ = fma(a.na[3], z3, tz_);                 \
-    tz_ = fma(a.na[2], z2, tz_);                 \
-    const double z0_ = fma(a.na[1], z1, tz_);    \
-    z4 = z3; z3 = z2; z2 = z1; z1 = z0_;         \
+// The recursions in software-pipelined form.  The reference's sample step is
+//     v0 = (((x + na4 v4) + na3 v3) + na2 v2) + na1 v1          y/b0 = (((x + cy4 v4) + cy3 v3) + cy2 v2) + cy1 v1
+// — per sample a chain of four dependent DFMA (33 cycles of latency) of which only the last link needs the newest
+// state.  Written that way the compiler issues the chain in order and a warp advances one sample per 33 cycles
+// (measured: the zero-state pass alone took 109 us for cfg2, an FP64 pipe busy 30 % of the time).  Here the partial
+// sums of the next three samples are carried in registers instead of the older states:
+//     pA = x[n]   + na4 v[n-4] + na3 v[n-3] + na2 v[n-2]     (complete but for the newest state)
+//     pB = x[n+1] + na4 v[n-3] + na3 v[n-2]
+//     pC = x[n+2] + na4 v[n-2]                  xh = x[n+3]
+// and one step is  v0 = fma(na1, v1, pA); pA = fma(na2, v1, pB); pB = fma(na3, v1, pC); pC = fma(na4, v1, xh):
+// four DFMA that depend on v1 only, the same additions in the same order (bit-identical results), a recurrence of
+// ONE DFMA per sample.  The output tap is pipelined the same way (yA, yB, yC).  Samples are consumed four ahead.
+#define SSBW_P2_INIT(x0, x1, x2, x3)                                                             \
+  double pA = fma(a.na[2], v2, fma(a.na[3], v3, fma(a.na[4], v4, (double)(x0))));                \
+  double pB = fma(a.na[3], v2, fma(a.na[4], v3, (double)(x1)));                                  \
+  double pC = fma(a.na[4], v2, (double)(x2));                                                    \
+  double yA = fma(a.cy[2], v2, fma(a.cy[3], v3, fma(a.cy[4], v4, (double)(x0))));                \
+  double yB = fma(a.cy[3], v2, fma(a.cy[4], v3, (double)(x1)));                                  \
+  double yC = fma(a.cy[4], v2, (double)(x2));                                                    \
+  double xh = (double)(x3);                                                                      \
+  float xd0 = (x0), xd1 = (x1), xd2 = (x2), xd3 = (x3);   /* x[n] .. x[n+3] for the peak detectors */
+// xs: the sample four ahead, x[n+4]; ACC(y) takes y[n] / b0
+#define SSBW_P2_STEP(xs, ACC)                                                                    \
+  {                                                                                              \
+    const float xf_ = xd0;                                                                       \
+    xd0 = xd1; xd1 = xd2; xd2 = xd3; xd3 = (xs);                                                 \
+    if (TPF != 0) sp = fmaxf(sp, fabsf(xf_));                                                    \
+    const double v0_ = fma(a.na[1], v1, pA);                                                     \
+    const double y_ = fma(a.cy[1], v1, yA);                                                      \
+    pA = fma(a.na[2], v1, pB); pB = fma(a.na[3], v1, pC); pC = fma(a.na[4], v1, xh);             \
+    yA = fma(a.cy[2], v1, yB); yB = fma(a.cy[3], v1, yC); yC = fma(a.cy[4], v1, xh);             \
+    xh = (double)(xs);                                                                           \
+    v1 = v0_;                                                                                    \
+    ACC(y_)                                                                                      \
+    SSBW_TP_STEP(xf_)                                                                            \
+  }
+#define SSBW_P1_INIT(x0, x1, x2, x3) \
+  double pA = (double)(x0), pB = (double)(x1), pC = (double)(x2), xh = (double)(x3);
+#define SSBW_P1_STEP(xs)                                                                         \
+  {                                                                                              \
+    const double z0_ = fma(a.na[1], z1, pA);                                                     \
+    pA = fma(a.na[2], z1, pB); pB = fma(a.na[3], z1, pC); pC = fma(a.na[4], z1, xh);             \
+    xh = (double)(xs);                                                                           \
+    z4 = z3; z3 = z2; z2 = z1; z1 = z0_;                                                         \
   }
 
 // One true-peak sample: ebur128's polyphase interpolator as f32 FMAs over the register window w2[t] = x[n-1-t]
@@ -210,15 +236,47 @@ __device__ __forceinline__ unsigned count_tasks(const PairGeom& gm) {
   return n_task;
 }
 
-// group g of my segment inside a stage: base of its 128-byte line and the swizzle key of its first quad
-#define SSBW_GROUP_ADDR(stage, g, grp, kk)                 \
-  const unsigned char* grp;                                \
-  int kk;                                                  \
-  {                                                        \
-    const int gb_ = q0 + (g) * W::U;                       \
-    const int rl_ = (gb_ >> 3) * W::R + rr;                \
-    grp = (stage) + (rl_ << 7);                            \
-    kk = (gb_ ^ rl_) & 7;                                  \
+// quad qd of stream rr inside a stage (lines past the tile are clamped: only lookahead samples that are never used
+// come from there)
+template <class W>
+__device__ __forceinline__ const unsigned char* quad_ptr(const unsigned char* stage, int rr, int qd) {
+  const int li = min(qd >> 3, W::NL - 1);
+  const int rl = li * W::R + rr;
+  return stage + (rl << 7) + (((qd ^ rl) & 7) << 4);
+}
+// The sample stream of a segment runs four samples (SHQ quads) ahead of the recursion.
+// Stereo: a lane needs ONE float (its channel) per frame, so it reads 4-byte words: the byte offset of its word in
+// quad chunk `ch` of line `la` is ((la * R + rr) << 7) + ((ch ^ key) << 4) + 4 c with key = (la * R + rr) & 7, i.e.
+// line_off ^ (ch << 4) with line_off = (rl << 7) ^ (key << 4) | 4 c — one XOR per quad, the second frame of the quad
+// at +8 (an immediate), no channel select.  A group's 8 quads are chunks 2..7 of line LA and chunks 0..1 of line
+// LA + 1 (segments start on line boundaries).  Mono: 4 quads per group, 16-byte loads, generic addressing.
+#define SSBW_GROUP_BASES(stage, g)                                                               \
+  unsigned offA_ = 0, offB_ = 0;                                                                 \
+  if (W::C == 2) {                                                                               \
+    const int la_ = (q0 >> 3) + (g), lb_ = min(la_ + 1, W::NL - 1);                              \
+    const unsigned ra_ = (unsigned)(la_ * W::R + rr), rb_ = (unsigned)(lb_ * W::R + rr);         \
+    const unsigned sb_ = smem_u32(stage);   /* 1 KB aligned: the XORs below touch bits 2..6 only */ \
+    offA_ = ((sb_ + (ra_ << 7)) ^ ((ra_ & 7u) << 4)) | ((unsigned)c << 2);                       \
+    offB_ = ((sb_ + (rb_ << 7)) ^ ((rb_ & 7u) << 4)) | ((unsigned)c << 2);                       \
+  }
+// sample f (0 .. FPQ-1) of quad j of group g, for this lane's channel
+#define SSBW_GROUP_SAMPLE(stage, g, j, f, qv)                                                                      \
+  (W::C == 2 ? *reinterpret_cast<const float*>(__cvta_shared_to_generic(((j) < 6 ? offA_ ^ (((j) + 2u) << 4) : offB_ ^ (((j) - 6u) << 4)) + 8u * (f))) \
+             : pickc<1>(qv, f, 0))
+#define SSBW_GROUP_QUADLOAD(stage, g, j)                                                                           \
+  (W::C == 2 ? make_float4(0.f, 0.f, 0.f, 0.f)                                                                     \
+             : *reinterpret_cast<const float4*>(quad_ptr<W>((stage), rr, q0 + W::SHQ + (g) * W::U + (j))))
+// the first four samples of my segment
+#define SSBW_FIRST4(stage, x0, x1, x2, x3)                                                       \
+  float x0, x1, x2, x3;                                                                          \
+  {                                                                                              \
+    const float4 qa_ = *reinterpret_cast<const float4*>(quad_ptr<W>((stage), rr, q0));           \
+    if (W::C == 2) {                                                                             \
+      const float4 qb_ = *reinterpret_cast<const float4*>(quad_ptr<W>((stage), rr, q0 + 1));     \
+      x0 = pickc<2>(qa_, 0, c); x1 = pickc<2>(qa_, 1, c); x2 = pickc<2>(qb_, 0, c); x3 = pickc<2>(qb_, 1, c); \
+    } else {                                                                                     \
+      x0 = qa_.x; x1 = qa_.y; x2 = qa_.z; x3 = qa_.w;                                            \
+    }                                                                                            \
   }
 
 template <class W, bool IS_B>
@@ -255,16 +313,21 @@ __device__ __forceinline__ void run_p1(const WArgs& a, unsigned char* stages, ui
       mbar_wait_warp(&full[g % kWStages], (g / kWStages) & 1);
       const unsigned char* st = stages + (size_t)(g % kWStages) * W::STAGE_STRIDE;
       double z1 = 0, z2 = 0, z3 = 0, z4 = 0;
+      {
+        SSBW_FIRST4(st, x0, x1, x2, x3)
+        SSBW_P1_INIT(x0, x1, x2, x3)
+#ifdef SSBW_DIAG_NO_P1
+        for (int gi = 0; gi < 0; gi++) {
+#else
 #pragma unroll 1
-      for (int gi = 0; gi < NG; gi++) {
-        SSBW_GROUP_ADDR(st, gi, grp, kk)
+        for (int gi = 0; gi < NG; gi++) {
+#endif
+          SSBW_GROUP_BASES(st, gi)
 #pragma unroll
-        for (int j = 0; j < W::U; j++) {
-          const float4 qn = *reinterpret_cast<const float4*>(grp + ((kk ^ j) << 4));
+          for (int j = 0; j < W::U; j++) {
+            const float4 qn = SSBW_GROUP_QUADLOAD(st, gi, j);
 #pragma unroll
-          for (int f = 0; f < W::FPQ; f++) {
-            const double xn = SSBW_CVT(pickc<C>(qn, f, c));
-            SSBW_ZERO_STEP(xn, z1, z2, z3, z4)
+            for (int f = 0; f < W::FPQ; f++) SSBW_P1_STEP(SSBW_GROUP_SAMPLE(st, gi, j, f, qn))
           }
         }
       }
@@ -365,7 +428,9 @@ __device__ __forceinline__ void run_p2(const WArgs& a, const CUtensorMap* tmap, 
       const double2 db = reinterpret_cast<const double2*>(dk_slot)[lane * 2 + 1];
       __syncwarp();
       if (lane == 0) mbar_arrive(dk_free);
+#ifndef SSBW_NO_SECOND_WAIT
       mbar_wait_warp(&full[g % kWStages], (g / kWStages) & 1);
+#endif
       double v1, v2, v3, v4;
       from_diff(da.x, da.y, db.x, db.y, v1, v2, v3, v4);
       const unsigned to_boundary = a.s100 - pos_tile;  // frames of this tile before the bucket boundary (>= F: none inside)
@@ -385,45 +450,39 @@ __device__ __forceinline__ void run_p2(const WArgs& a, const CUtensorMap* tmap, 
           w2[t] = make_float2(wv, wv);
         }
       }
-      if (!mixed) {
+      {
+        SSBW_FIRST4(st0, x0, x1, x2, x3)
+        SSBW_P2_INIT(x0, x1, x2, x3)
+        if (!mixed) {
+#define SSBW_ACC_FAST(y) acc = fma((y), (y), acc);
+#ifdef SSBW_DIAG_NO_P2
+          for (int gi = 0; gi < 0; gi++) {
+#else
 #pragma unroll 1
-        for (int gi = 0; gi < NG; gi++) {
-          SSBW_GROUP_ADDR(st0, gi, grp, kk)
-          double acc = 0.0;
+          for (int gi = 0; gi < NG; gi++) {
+#endif
+            SSBW_GROUP_BASES(st0, gi)
+            double acc = 0.0;
 #pragma unroll
-          for (int j = 0; j < W::U; j++) {
-            const float4 qv = *reinterpret_cast<const float4*>(grp + ((kk ^ j) << 4));
+            for (int j = 0; j < W::U; j++) {
+              const float4 qv = SSBW_GROUP_QUADLOAD(st0, gi, j);
 #pragma unroll
-            for (int f = 0; f < W::FPQ; f++) {
-              const float xf = pickc<C>(qv, f, c);
-              if (TPF != 0) sp = fmaxf(sp, fabsf(xf));
-              const double xd = SSBW_CVT(xf);
-              SSBW_FILTER_STEP(xd)
-              acc = fma(y_, y_, acc);
-              SSBW_TP_STEP(xf)
+              for (int f = 0; f < W::FPQ; f++) SSBW_P2_STEP(SSBW_GROUP_SAMPLE(st0, gi, j, f, qv), SSBW_ACC_FAST)
             }
+            if (16 * (gi + 1) <= lb) accA += acc; else accB += acc;
           }
-          if (16 * (gi + 1) <= lb) accA += acc; else accB += acc;
-        }
-      } else {
-        // a bucket boundary strictly inside some lane's group (rates whose 100 ms is not whole tiles): per-sample test
-        int i_ = 0;
+#undef SSBW_ACC_FAST
+        } else {
+          // a bucket boundary strictly inside some lane's group (rates whose 100 ms is not whole tiles): per-sample test
+          int i_ = 0;
+#define SSBW_ACC_SLOW(y) if (i_ < lb) accA = fma((y), (y), accA); else accB = fma((y), (y), accB); i_++;
 #pragma unroll 1
-        for (int gi = 0; gi < NG; gi++) {
-          SSBW_GROUP_ADDR(st0, gi, grp, kk)
-#pragma unroll 1
-          for (int j = 0; j < W::U; j++) {
-            const float4 qv = *reinterpret_cast<const float4*>(grp + ((kk ^ j) << 4));
+          for (int qi = 0; qi < W::NQ; qi++) {
+            const float4 qv = *reinterpret_cast<const float4*>(quad_ptr<W>(st0, rr, q0 + W::SHQ + qi));
 #pragma unroll
-            for (int f = 0; f < W::FPQ; f++, i_++) {
-              const float xf = pickc<C>(qv, f, c);
-              if (TPF != 0) sp = fmaxf(sp, fabsf(xf));
-              const double xd = SSBW_CVT(xf);
-              SSBW_FILTER_STEP(xd)
-              if (i_ < lb) accA = fma(y_, y_, accA); else accB = fma(y_, y_, accB);
-              SSBW_TP_STEP(xf)
-            }
+            for (int f = 0; f < W::FPQ; f++) SSBW_P2_STEP(pickc<C>(qv, f, c), SSBW_ACC_SLOW)
           }
+#undef SSBW_ACC_SLOW
         }
       }
       // ---- the tile is done: FIR history, stage back to the TMA ring (the tile three ahead, possibly the next pass's),
@@ -464,14 +523,22 @@ __device__ __forceinline__ void run_p2(const WArgs& a, const CUtensorMap* tmap, 
     }
   }
 }
-#undef SSBW_GROUP_ADDR
+#undef SSBW_GROUP_BASES
+#undef SSBW_GROUP_SAMPLE
+#undef SSBW_GROUP_QUADLOAD
+#undef SSBW_FIRST4
 
 // MIXED: type A = (T 4, L 80), type B = (T 5, L 64), 320-frame tiles, 28 stereo streams per pass;
 // !MIXED: every set (T 4, L 64), 256-frame tiles, 32 stereo streams per pass.
 template <int C, bool MIXED>
 struct WCfg {
+#ifdef SSBW_UNIFORM_L80   // experiment: both set types T = 4, L = 80 (4 + 3 streams): equal steps per tile, 11 % more FP64 work
+  using A = WType<C, 4, 8 / C, MIXED ? 80 : 64>;
+  using B = WType<C, 4, (MIXED ? 6 : 8) / C, MIXED ? 80 : 64>;
+#else
   using A = WType<C, 4, 8 / C, MIXED ? 80 : 64>;
   using B = WType<C, MIXED ? 5 : 4, (MIXED ? 6 : 8) / C, 64>;
+#endif
   static_assert(A::F == B::F, "both set types walk the same tiles");
   static constexpr int F = A::F;
   static constexpr int CAP = 4 * A::R + 4 * B::R;  // streams per CTA pass
@@ -538,8 +605,10 @@ k_loudness_wtile(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     gather_block_done(ra.ga);
   }
 }
-#undef SSBW_FILTER_STEP
-#undef SSBW_ZERO_STEP
+#undef SSBW_P2_INIT
+#undef SSBW_P2_STEP
+#undef SSBW_P1_INIT
+#undef SSBW_P1_STEP
 #undef SSBW_TP_STEP
 #undef SSBW_CVT
 
@@ -595,8 +664,8 @@ cudaError_t launch_shape(const LoudParams& p, const LoudState& st, const float* 
       !encode_box<typename Cfg::B>(&tB, d_in, st.n_streams, row_floats, used_floats))
     return cudaErrorInvalidValue;
   memcpy(a.PA, Cfg::A::L == 80 ? p.handoff80 : p.handoff, sizeof(a.PA));   // cached per meter (init_meter)
-  memcpy(a.PB, p.handoff, sizeof(a.PB));
-  static_assert(Cfg::B::L == 64 && (Cfg::A::L == 80 || Cfg::A::L == 64), "hand-off matrices cached for 64 and 80 frames");
+  memcpy(a.PB, Cfg::B::L == 80 ? p.handoff80 : p.handoff, sizeof(a.PB));
+  static_assert((Cfg::B::L == 64 || Cfg::B::L == 80) && (Cfg::A::L == 80 || Cfg::A::L == 64), "hand-off matrices cached for 64 and 80 frames");
   a.n_tiles = (unsigned)n_tiles;
   const unsigned n_ctas = (unsigned)(st.n_streams < (size_t)sm_count ? st.n_streams : (size_t)sm_count);
   // 4 / 2: true-peak FIR (ebur128's rate rule) + sample peak; 1: sample peak only; 0: neither

@@ -65,6 +65,7 @@ struct ssb_analyzer {
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
+  int32_t tick_fft_status[2] = {0, 0};  // mid / side get_fft statuses of the last process_tick / mic_tick
   char err[256] = {0};
 };
 

@@ -418,3 +418,39 @@ def test_one_shot_silence_and_dc_steps(ssb, oracle, cuda):
     assert a.calculate_integrated_lufs(2, z) == -np.inf
     z[48000 * 2 * 13:48000 * 2 * 14] = 0.5          # one second of DC inside silence: the high-pass tail crosses a chunk boundary
     assert abs(a.calculate_integrated_lufs(2, z) - o.calculate_integrated_lufs(2, z)) <= 1e-9
+
+
+@pytest.mark.parametrize("n,channels,rate,frames,mode_name", [
+    (16384, 2, 48000, 9600, "MODE_ALL"),        # default dispatch: k_loudness_rows (>= 16384 streams), 4x true peak
+    (20000, 2, 48000, 4800 + 64, "MODE_LOUDNESS"),
+    (16384, 6, 96000, 9600, "MODE_ALL"),        # BASELINE config 5's per-GPU shape: k_loudness_rows_any, 2x true peak
+])
+def test_default_dispatch_at_scale_matches_oracle_subset(ssb, oracle, cuda, n, channels, rate, frames, mode_name):
+    """the kernels the dispatcher picks by itself at BASELINE's stream counts, checked against the
+    oracle on a subset of streams (inputs generated on the device, the subset copied to the host for the oracle)."""
+    import bench
+    torch = cuda
+    dev = torch.device("cuda", 0)
+    mode = getattr(ssb, mode_name)
+    b = ssb.BatchAnalyzer(n, channels, rate, mode)          # no force_kernel: automatic dispatch
+    sub = np.unique(np.concatenate([np.arange(0, n, n // 61), [n - 1, n - 2, 127, 128, 129]]))
+    ob = oracle.Batch(len(sub), channels, rate, getattr(oracle, mode_name))
+    reps = 3
+    for k in range(reps):
+        x = bench.make_input_device_chunked(torch, n, frames, 900 + 31 * k, dev, chunk=2048, channels=channels, rate=rate)
+        b.add_frames_device(x)
+        ob.add_frames(np.ascontiguousarray(x[torch.from_numpy(sub).to(dev)].cpu().numpy()))
+        del x
+    want = ob.query()
+    assert close_lu(b.loudness_global()[sub], want["global"])
+    assert close_lu(b.loudness_range()[sub], want["range"])
+    if (frames * reps) % ((rate + 5) // 10) == 0:
+        assert close_lu(b.loudness_momentary()[sub], want["momentary"], 1e-9)
+        assert close_lu(b.loudness_shortterm()[sub], want["shortterm"], 1e-9)
+    if mode_name == "MODE_ALL":
+        assert np.all(np.abs(b.true_peak()[sub] - want["true_peak"]) <= TP_RTOL * want["true_peak"])
+    for j in (0, len(sub) // 2, len(sub) - 1):
+        hb, hs = b.histograms(int(sub[j]))
+        ob_b, ob_s = ob._per_stream_hist(j)
+        assert np.array_equal(hb, ob_b) and np.array_equal(hs, ob_s)
+    assert np.all(np.isfinite(b.loudness_global()))

