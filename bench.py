@@ -298,8 +298,17 @@ def timed_device_leg(env, S, an, xs, gather, K, W, launches_per_step, clocks=Non
     ms_total = env.max_over_ranks(e0.elapsed_time(e1))
     launches = an.launches - l0
     filt_ms, filt_n = an.profile_read()
+    # the filter phase alone: the same kernel launched without its gating / results epilogue (feed only), same inputs
+    for i in range(3):
+        an.add_frames_device(xs[i & 1])
+    env.torch.cuda.synchronize()
+    an.profile(True)
+    for i in range(launches_per_step * 2):
+        an.add_frames_device(xs[i & 1])
+    fo_ms, fo_n = an.profile_read()
     an.profile(False)
-    return {"ms_total": ms_total, "launches": int(launches), "kernel_ms": filt_ms / max(filt_n, 1), "kernel_launches": int(filt_n)}
+    return {"ms_total": ms_total, "launches": int(launches), "kernel_ms": filt_ms / max(filt_n, 1), "kernel_launches": int(filt_n),
+            "filter_only_ms": fo_ms / max(fo_n, 1)}
 
 
 def timed_e2e_leg(env, an, hx, K, W, launches_per_step, pcm_fmt=None):
@@ -325,13 +334,20 @@ def timed_e2e_leg(env, an, hx, K, W, launches_per_step, pcm_fmt=None):
     return env.max_over_ranks(time.perf_counter() - t0)
 
 
-def roofline_block(kernel_ms, bytes_per_launch, peak, peak_kind, traffic, kernel_name):
+def roofline_block(kernel_ms, bytes_per_launch, peak, peak_kind, traffic, kernel_name, filter_only_ms=None):
+    """`achieved` / `frac` are for the kernel of the timed region — the fused launch: K-weighting filter + gating + per-stream
+    result rows.  `filter_phase_*` is the same kernel launched without that epilogue (what round 1's separate filter kernel
+    was), measured right after the timed region on the same inputs."""
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9 if kernel_ms else None
-    return {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-            "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "kernel_ms": kernel_ms,
-            "algorithmic_bytes_per_launch": bytes_per_launch,
-            "binding_resource": "FP64 issue (13 DFMA per sample with the time-segmentation pass), not HBM: see DESIGN.md section 3.1"}
+    out = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+           "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+           "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "kernel_ms": kernel_ms,
+           "algorithmic_bytes_per_launch": bytes_per_launch,
+           "binding_resource": "FP64 pipe + issue + shared-memory wavefronts all ~60-67 % busy (13 DFMA per sample with the time-segmentation pass), not HBM: DESIGN.md section 3.1"}
+    if filter_only_ms:
+        fo = bytes_per_launch / (filter_only_ms * 1e-3) / 1e9
+        out.update({"filter_phase_ms": filter_only_ms, "filter_phase_achieved": fo, "filter_phase_frac": fo / peak})
+    return out
 
 
 def traffic_of(key):
@@ -429,14 +445,16 @@ def run_ours(args):
         "e2e": e2e["loudness"],
         "gpu_launches": L["launches"],
         "roofline": roofline_block(L["kernel_ms"], samples_per_launch * 4, peak, peak_kind,
-                                   traffic_of("filter_kernel_dram_bytes_per_launch"), "k_loudness_wtile<2,0> (K-weighting + 100 ms energy buckets + gating/results epilogue)"),
+                                   traffic_of("filter_kernel_dram_bytes_per_launch"), "k_loudness_wtile<2,0> (K-weighting + 100 ms energy buckets + gating/results epilogue)",
+                                   L["filter_only_ms"]),
         "cpu_baseline": cpu,
         "ms_per_launch": L["ms_total"] / K / LPS, "launch_overhead_us": (L["ms_total"] / K / LPS - L["kernel_ms"]) * 1e3,
         "gather": L["gather"],
         # ---- Mode::all(): what the reference's Analyzer always runs (analyzer.rs:36,51,171) ----
         "value_all": value_all, "ms_per_step_all": A["ms_total"] / K, "gpu_launches_all": A["launches"],
         "roofline_all": roofline_block(A["kernel_ms"], samples_per_launch * 4, peak, peak_kind,
-                                       traffic_of("filter_kernel_all_dram_bytes_per_launch"), "k_loudness_wtile<2,4> (adds sample peak + 4x true-peak FIR, 36 f32 FMA per sample)"),
+                                       traffic_of("filter_kernel_all_dram_bytes_per_launch"), "k_loudness_wtile<2,4> (adds sample peak + 4x true-peak FIR, 36 f32 FMA per sample)",
+                                       A["filter_only_ms"]),
         "e2e_all": e2e["all"], "cpu_baseline_all": cpu_all,
         "e2e_s16": e2e_s16,
         "extras": extras,

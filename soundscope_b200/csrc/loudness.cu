@@ -256,7 +256,7 @@ k_results(const __grid_constant__ GateParams g, const __grid_constant__ ResultsA
   const int lane = threadIdx.x & 31;
   if (s < n_streams) {
     if (V == 0) results_for_stream_v0(g, ra, s, lane);
-    else results_for_stream(g, ra, s, lane);
+    else results_for_stream(g, ra, ra.energies, ra.bounds, s, lane);
   }
   gather_block_done(ra.ga);
 }
@@ -280,8 +280,9 @@ cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t bu
     ra.ga = *ga;
     ra.ga.n_blocks = blocks;
   }
-  // SSB_RESULTS_V: 0 = round-1 ordering, 1 = loads first (default), 2 = loads first capped at 128 registers (A/B timing)
-  static const int variant = [] { const char* e = getenv("SSB_RESULTS_V"); return e ? atoi(e) : 1; }();
+  // SSB_RESULTS_V (A/B timing): 0 = round-1 ordering, 1 = loads first, 2 = loads first capped at 128 registers (default:
+  // 16 resident warps per SM instead of 12; measured 38 us against 54 us per 4096-stream query after a cfg2 launch)
+  static const int variant = [] { const char* e = getenv("SSB_RESULTS_V"); return e ? atoi(e) : 2; }();
   if (variant == 0) k_results<0><<<blocks, tpb, 0, s>>>(g, ra, st.n_streams);
   else if (variant == 2) k_results<2><<<blocks, tpb, 0, s>>>(g, ra, st.n_streams);
   else k_results<1><<<blocks, tpb, 0, s>>>(g, ra, st.n_streams);

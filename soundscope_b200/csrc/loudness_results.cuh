@@ -87,7 +87,11 @@ __device__ __forceinline__ double ring_energy(const double* __restrict__ rg, con
 // histogram in memory with a fire-and-forget atomic and to this call's sums directly (the lane that gated it adds its
 // bin's energy to its partial sums; a new short-term entry is patched into the register copy), so nothing is read back
 // and no fence is needed.
-__device__ __forceinline__ void results_for_stream(const GateParams& g, const ResultsArgs& ra, const size_t s, const int lane) {
+// `energies` / `bounds`: the 1000 bin-centre energies and 1001 bin boundaries — ra.energies / ra.bounds, or a copy of
+// them in shared memory (the fused epilogue of k_loudness_wtile: with 225 KB of the SM's 228 KB carved out as shared
+// memory there is no L1 left, and every table lookup of the gating / percentile code would be an L2 round trip).
+__device__ __forceinline__ void results_for_stream(const GateParams& g, const ResultsArgs& ra, const double* __restrict__ energies,
+                                                   const double* __restrict__ bounds, const size_t s, const int lane) {
   const int C = g.channels;
   const size_t stride = 4 + 2 * (size_t)C;
   double* o = ra.out + s * stride;
@@ -104,11 +108,11 @@ __device__ __forceinline__ void results_for_stream(const GateParams& g, const Re
     for (uint64_t j = ra.gate_first + lane; j <= ra.gate_last; j += 32) {
       if (g.do_i && j >= 3) {
         const double e = window_energy(bkp, g, j, 4);
-        if (e >= ra.bounds[0]) atomicAdd(&ra.block_hist_rw[s * kHistBins + find_histogram_index(ra.bounds, e)], 1u);
+        if (e >= bounds[0]) atomicAdd(&ra.block_hist_rw[s * kHistBins + find_histogram_index(bounds, e)], 1u);
       }
       if (g.do_lra && j >= 29 && (j - 29) % 10 == 0) {
         const double e = window_energy(bkp, g, j, 30);
-        if (e >= ra.bounds[0]) atomicAdd(&ra.st_hist_rw[s * kHistBins + find_histogram_index(ra.bounds, e)], 1u);
+        if (e >= bounds[0]) atomicAdd(&ra.st_hist_rw[s * kHistBins + find_histogram_index(bounds, e)], 1u);
       }
     }
     __threadfence();
@@ -135,15 +139,15 @@ __device__ __forceinline__ void results_for_stream(const GateParams& g, const Re
     if (j <= ra.gate_last) {
       if (g.do_i && j >= 3) {
         const double e = window_energy(bkp, g, j, 4);
-        if (e >= ra.bounds[0]) {
-          my_b = find_histogram_index(ra.bounds, e);
+        if (e >= bounds[0]) {
+          my_b = find_histogram_index(bounds, e);
           atomicAdd(&ra.block_hist_rw[s * kHistBins + my_b], 1u);
         }
       }
       if (g.do_lra && j >= 29 && (j - 29) % 10 == 0) {
         const double e = window_energy(bkp, g, j, 30);
-        if (e >= ra.bounds[0]) {
-          my_s = find_histogram_index(ra.bounds, e);
+        if (e >= bounds[0]) {
+          my_s = find_histogram_index(bounds, e);
           atomicAdd(&ra.st_hist_rw[s * kHistBins + my_s], 1u);
         }
       }
@@ -177,10 +181,10 @@ __device__ __forceinline__ void results_for_stream(const GateParams& g, const Re
     unsigned long long cnt = 0;
 #pragma unroll
     for (int t = 0; t < 32; t++) {
-      if (hi_[t]) pw = fma((double)hi_[t], ra.energies[bin0 + t], pw);
+      if (hi_[t]) pw = fma((double)hi_[t], energies[bin0 + t], pw);
       cnt += hi_[t];
     }
-    const double my_e = my_b >= 0 ? ra.energies[my_b] : 0.0;   // the block this lane has just gated
+    const double my_e = my_b >= 0 ? energies[my_b] : 0.0;   // the block this lane has just gated
     if (my_b >= 0) { pw += my_e; cnt += 1; }
     pw = warp_sum(pw);
     cnt = warp_sum_u64(cnt);
@@ -189,17 +193,17 @@ __device__ __forceinline__ void results_for_stream(const GateParams& g, const Re
       double rel = pw / (double)cnt;
       rel *= 0.1;  // 10^(-10/10)
       int start;
-      if (rel < ra.bounds[0]) start = 0;
+      if (rel < bounds[0]) start = 0;
       else {
-        start = find_histogram_index(ra.bounds, rel);
-        if (rel > ra.energies[start]) ++start;
+        start = find_histogram_index(bounds, rel);
+        if (rel > energies[start]) ++start;
       }
       double gp = 0.0;
       unsigned long long gc = 0;
 #pragma unroll
       for (int t = 0; t < 32; t++) {
         if (hi_[t] && bin0 + t >= start) {
-          gp = fma((double)hi_[t], ra.energies[bin0 + t], gp);
+          gp = fma((double)hi_[t], energies[bin0 + t], gp);
           gc += hi_[t];
         }
       }
@@ -225,7 +229,7 @@ __device__ __forceinline__ void results_for_stream(const GateParams& g, const Re
     unsigned long long cnt = 0;
 #pragma unroll
     for (int t = 0; t < 32; t++) {
-      if (hl_[t]) pw = fma((double)hl_[t], ra.energies[bin0 + t], pw);
+      if (hl_[t]) pw = fma((double)hl_[t], energies[bin0 + t], pw);
       cnt += hl_[t];
     }
     pw = warp_sum(pw);
@@ -234,10 +238,10 @@ __device__ __forceinline__ void results_for_stream(const GateParams& g, const Re
     else {
       const double stl_integrated = 0.01 * (pw / (double)cnt);  // 10^(-20/10)
       int index;
-      if (stl_integrated < ra.bounds[0]) index = 0;
+      if (stl_integrated < bounds[0]) index = 0;
       else {
-        index = find_histogram_index(ra.bounds, stl_integrated);
-        if (stl_integrated > ra.energies[index]) ++index;
+        index = find_histogram_index(bounds, stl_integrated);
+        if (stl_integrated > energies[index]) ++index;
       }
       // lane totals above the relative gate, their exclusive prefix, and the grand total
       unsigned long long mine = 0;
@@ -273,7 +277,7 @@ __device__ __forceinline__ void results_for_stream(const GateParams& g, const Re
           lo_bin = max(lo_bin, __shfl_xor_sync(0xffffffffu, lo_bin, o2));
           hi_bin = max(hi_bin, __shfl_xor_sync(0xffffffffu, hi_bin, o2));
         }
-        lra = energy_to_loudness(ra.energies[hi_bin]) - energy_to_loudness(ra.energies[lo_bin]);
+        lra = energy_to_loudness(energies[hi_bin]) - energy_to_loudness(energies[lo_bin]);
       }
     }
   }

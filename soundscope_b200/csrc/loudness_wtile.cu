@@ -279,11 +279,13 @@ __device__ __forceinline__ const unsigned char* quad_ptr(const unsigned char* st
     }                                                                                            \
   }
 
-template <class W, bool IS_B>
+template <class W, bool IS_B, int TPF>
 __device__ __forceinline__ void run_p1(const WArgs& a, unsigned char* stages, uint64_t* full, uint64_t* dk_full,
                                        uint64_t* dk_free, double* dk_slot, const PairGeom gm, const int lane) {
   constexpr int C = W::C, T = W::T, Q = W::Q, L = W::L;
   constexpr int NG = L / 16;
+  constexpr int TPW = TPF == 4 ? 11 : (TPF == 2 ? 23 : 1);  // true-peak FIR history length
+  static_assert(TPW <= L, "the FIR history of a segment lies inside the previous one");
 #define SSBW_P(i) (IS_B ? a.PB[i] : a.PA[i])
   const unsigned n_task = count_tasks<W>(gm);
   if (n_task * a.n_tiles == 0) return;
@@ -308,14 +310,33 @@ __device__ __forceinline__ void run_p1(const WArgs& a, unsigned char* stages, ui
       const double* f = a.filt + gidx * 4;
       to_diff(f[0], f[1], f[2], f[3], e0, e1, e2, e3);
     }
+    // The peak detectors depend on the input only, so they ride with this (lighter) pass: sample peak and the polyphase
+    // true-peak FIR over the register window w2[t] = x[n-1-t]
+    float sp = 0.f, tp = 0.f;
+    float hist[TPW];   // the TPW samples before the next tile (meaningful in the k == 0 lanes)
+#pragma unroll
+    for (int t = 0; t < TPW; t++) hist[t] = (TPF >= 2 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
     for (unsigned tile = 0; tile < a.n_tiles; tile++) {
       const unsigned g = g0 + tile;
       mbar_wait_warp(&full[g % kWStages], (g / kWStages) & 1);
       const unsigned char* st = stages + (size_t)(g % kWStages) * W::STAGE_STRIDE;
       double z1 = 0, z2 = 0, z3 = 0, z4 = 0;
+      // FIR window: the TPW samples before my segment (previous segment's tail in the same tile, or, for the first
+      // segment, the previous tile's tail carried in `hist`); both halves equal so a tap feeds two phases in one FFMA2
+      float2 w2[TPW];
+      if (TPF >= 2) {
+#pragma unroll
+        for (int t = 0; t < TPW; t++) {
+          const int fr = k > 0 ? k * L - 1 - t : 0;
+          const float prev = *reinterpret_cast<const float*>(float_addr<W>(st, rr, fr * C + c));
+          const float wv = k > 0 ? prev : hist[t];
+          w2[t] = make_float2(wv, wv);
+        }
+      }
       {
         SSBW_FIRST4(st, x0, x1, x2, x3)
         SSBW_P1_INIT(x0, x1, x2, x3)
+        float xd0 = x0, xd1 = x1, xd2 = x2, xd3 = x3;   // x[n] .. x[n+3] for the peak detectors
 #ifdef SSBW_DIAG_NO_P1
         for (int gi = 0; gi < 0; gi++) {
 #else
@@ -327,9 +348,23 @@ __device__ __forceinline__ void run_p1(const WArgs& a, unsigned char* stages, ui
           for (int j = 0; j < W::U; j++) {
             const float4 qn = SSBW_GROUP_QUADLOAD(st, gi, j);
 #pragma unroll
-            for (int f = 0; f < W::FPQ; f++) SSBW_P1_STEP(SSBW_GROUP_SAMPLE(st, gi, j, f, qn))
+            for (int f = 0; f < W::FPQ; f++) {
+              const float xs_ = SSBW_GROUP_SAMPLE(st, gi, j, f, qn);
+              SSBW_P1_STEP(xs_)
+              if (TPF != 0) {
+                const float xf_ = xd0;
+                xd0 = xd1; xd1 = xd2; xd2 = xd3; xd3 = xs_;
+                sp = fmaxf(sp, fabsf(xf_));
+                SSBW_TP_STEP(xf_)
+              }
+            }
           }
         }
+      }
+      if (TPF >= 2) {
+        // the last segment's tail is the history of the next tile's first segment
+#pragma unroll
+        for (int t = 0; t < TPW; t++) hist[t] = __shfl_sync(0xffffffffu, w2[t].x, (T - 1) * Q + q);
       }
       // hand-off: lane k keeps the carry after k links as its own start state; after T links e is the next tile's carry
       double zd0, zd1, zd2, zd3;
@@ -365,18 +400,28 @@ __device__ __forceinline__ void run_p1(const WArgs& a, unsigned char* stages, ui
       f[2] = fabs(c3) < tiny ? 0.0 : c3;
       f[3] = fabs(c4) < tiny ? 0.0 : c4;
     }
+    sp = seg_max<W>(sp, q);
+    tp = seg_max<W>(tp, q);
+    if (row_ok && k == 0) {
+      if (TPF != 0) a.speak[gidx] = fmaxf(a.speak[gidx], sp);
+      if (TPF >= 2) {
+        a.tpeak[gidx] = fmaxf(a.tpeak[gidx], tp);
+#pragma unroll
+        for (int t = 0; t < TPW; t++) a.tphist[gidx * kTpHist + t] = hist[t];
+      }
+    }
   }
 #undef SSBW_P
 }
 
-template <class W, int TPF>
+template <class W>
 __device__ __forceinline__ void run_p2(const WArgs& a, const CUtensorMap* tmap, unsigned char* stages, uint64_t* full,
                                        uint64_t* dk_full, uint64_t* dk_free, const double* dk_slot, const PairGeom gm,
                                        const int lane) {
   constexpr int C = W::C, T = W::T, Q = W::Q, L = W::L, F = W::F;
   constexpr int NG = L / 16;
-  constexpr int TPW = TPF == 4 ? 11 : (TPF == 2 ? 23 : 1);  // true-peak FIR history length
-  static_assert(L % 16 == 0 && TPW <= L, "segments are whole groups; the FIR history of a segment lies inside the previous one");
+  constexpr int TPF = 0;   // the peak detectors live in the P1 warp
+  static_assert(L % 16 == 0, "segments are whole groups");
   const unsigned n_task = count_tasks<W>(gm);
   const unsigned total_tiles = n_task * a.n_tiles;
   if (total_tiles == 0) return;
@@ -413,10 +458,10 @@ __device__ __forceinline__ void run_p2(const WArgs& a, const CUtensorMap* tmap, 
     double acc_cur = 0.0;  // owner lane: running sum (already times b0^2) of the bucket in progress
     unsigned slot = a.slot0;
     if (owner && live && a.pos0 > 0) acc_cur = a.bucket[gidx * kNB + slot];
-    float sp = 0.f, tp = 0.f;
-    float hist[TPW];   // the TPW samples before the next tile, hist[t] = x[n-1-t] (meaningful in the k == 0 lanes)
-#pragma unroll
-    for (int t = 0; t < TPW; t++) hist[t] = (TPF >= 2 && row_ok) ? a.tphist[gidx * kTpHist + t] : 0.f;
+    float sp = 0.f, tp = 0.f;   // unused here (TPF == 0): the step macro is shared with the peak-carrying pass
+    constexpr int TPW = 1;
+    float2 w2[TPW];
+    w2[0] = make_float2(0.f, 0.f);
     unsigned pos_tile = a.pos0;   // position of the tile start inside the bucket in progress
 
     for (unsigned tile = 0; tile < a.n_tiles; tile++) {
@@ -438,18 +483,6 @@ __device__ __forceinline__ void run_p2(const WArgs& a, const CUtensorMap* tmap, 
       lb = lb < 0 ? 0 : (lb > L ? L : lb);
       const unsigned mixed = __reduce_or_sync(0xffffffffu, (unsigned)(lb & 15));  // a boundary strictly inside a group
       double accA = 0.0, accB = 0.0;
-      // FIR window: the TPW samples before my segment (previous segment's tail in the same tile, or, for the first
-      // segment, the previous tile's tail carried in `hist`); both halves equal so a tap feeds two phases in one FFMA2
-      float2 w2[TPW];
-      if (TPF >= 2) {
-#pragma unroll
-        for (int t = 0; t < TPW; t++) {
-          const int fr = k > 0 ? k * L - 1 - t : 0;
-          const float prev = *reinterpret_cast<const float*>(float_addr<W>(st0, rr, fr * C + c));
-          const float wv = k > 0 ? prev : hist[t];
-          w2[t] = make_float2(wv, wv);
-        }
-      }
       {
         SSBW_FIRST4(st0, x0, x1, x2, x3)
         SSBW_P2_INIT(x0, x1, x2, x3)
@@ -487,10 +520,6 @@ __device__ __forceinline__ void run_p2(const WArgs& a, const CUtensorMap* tmap, 
       }
       // ---- the tile is done: FIR history, stage back to the TMA ring (the tile three ahead, possibly the next pass's),
       //      bucket sums (fixed-order reduction over the segments, times b0^2) ----
-      if (TPF >= 2) {
-#pragma unroll
-        for (int t = 0; t < TPW; t++) hist[t] = __shfl_sync(0xffffffffu, w2[t].x, (T - 1) * Q + q);
-      }
       __syncwarp();
       if (lane == 0 && g + kWStages < total_tiles) issue(g + kWStages);
       const double sA = seg_sum<W>(accA, q);
@@ -510,17 +539,8 @@ __device__ __forceinline__ void run_p2(const WArgs& a, const CUtensorMap* tmap, 
     }
 
     // ---------------- end of this pair's streams for this pass: bucket in progress, peaks ----------------
-    sp = seg_max<W>(sp, q);
-    tp = seg_max<W>(tp, q);
-    if (owner) {
-      a.bucket[gidx * kNB + slot] = live ? acc_cur : 0.0;
-      if (TPF != 0) a.speak[gidx] = fmaxf(a.speak[gidx], sp);
-      if (TPF >= 2) {
-        a.tpeak[gidx] = fmaxf(a.tpeak[gidx], tp);
-#pragma unroll
-        for (int t = 0; t < TPW; t++) a.tphist[gidx * kTpHist + t] = hist[t];
-      }
-    }
+    (void)sp; (void)tp; (void)w2;
+    if (owner) a.bucket[gidx * kNB + slot] = live ? acc_cur : 0.0;
   }
 }
 #undef SSBW_GROUP_BASES
@@ -588,20 +608,24 @@ k_loudness_wtile(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     if (pair < 4) {
       unsigned char* stages = smem + (size_t)pair * kWStages * WA::STAGE_STRIDE;
       gm.warp_off = (unsigned)pair * WA::R;
-      if (is_p1) run_p1<WA, false>(a, stages, full, full + 3, full + 4, dk_slot, gm, lane);
-      else run_p2<WA, TPF>(a, &tmapA, stages, full, full + 3, full + 4, dk_slot, gm, lane);
+      if (is_p1) run_p1<WA, false, TPF>(a, stages, full, full + 3, full + 4, dk_slot, gm, lane);
+      else run_p2<WA>(a, &tmapA, stages, full, full + 3, full + 4, dk_slot, gm, lane);
     } else {
       unsigned char* stages = smem + (size_t)4 * kWStages * WA::STAGE_STRIDE + (size_t)(pair - 4) * kWStages * WB::STAGE_STRIDE;
       gm.warp_off = 4u * WA::R + (unsigned)(pair - 4) * WB::R;
-      if (is_p1) run_p1<WB, true>(a, stages, full, full + 3, full + 4, dk_slot, gm, lane);
-      else run_p2<WB, TPF>(a, &tmapB, stages, full, full + 3, full + 4, dk_slot, gm, lane);
+      if (is_p1) run_p1<WB, true, TPF>(a, stages, full, full + 3, full + 4, dk_slot, gm, lane);
+      else run_p2<WB>(a, &tmapB, stages, full, full + 3, full + 4, dk_slot, gm, lane);
     }
   }
   if (a.fused_results) {
     // gating + result rows of this CTA's streams (analyzer.rs:147-164), one warp per stream; the bucket sums and peaks
     // written above by other warps of this CTA are visible after the barrier
     __syncthreads();
-    for (unsigned r = warp; r < cta_rows; r += kWWarps) results_for_stream(g, ra, (size_t)row0 + r, lane);
+    // the histogram tables (energies[1000] | boundaries[1001], contiguous) into the now idle stage memory
+    double* tab = reinterpret_cast<double*>(smem);
+    for (int i = threadIdx.x; i < 2 * kHistBins + 1; i += kWWarps * 32) tab[i] = __ldg(ra.energies + i);
+    __syncthreads();
+    for (unsigned r = warp; r < cta_rows; r += kWWarps) results_for_stream(g, ra, tab, tab + kHistBins, (size_t)row0 + r, lane);
     gather_block_done(ra.ga);
   }
 }

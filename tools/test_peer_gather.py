@@ -19,6 +19,8 @@ for mode, force in ((S.MODE_LOUDNESS, 0), (S.MODE_ALL, 0), (S.MODE_ALL, 1)):   #
     an.force_kernel(force)
     g = PeerGather(an, world=world, rank=rank, allow_p2p=os.environ.get("NO_P2P") is None)
     refs = [S.BatchAnalyzer(n, ch, rate, mode, device=local) for _ in range(world)]
+    for r_ in refs:
+        r_.force_kernel(force)   # same kernel as the analyzer under test: rows are compared bit for bit
     for step in range(4):
         for l in range(3):
             x = make_input_device(torch, n, frames, 100 * rank + 10 * step + l, dev)
