@@ -142,7 +142,8 @@ int32_t ssb_add_frames_f32_device_results(ssb_analyzer* h, const float* d_interl
  *   (exchange the handles through your process group)
  *   ssb_gather_open(h, handles)                   handles = world x 64 bytes in rank order (own slot ignored)
  *   ... every ssb_results_device / ssb_add_frames_f32_device_results now also publishes into parity `p` ...
- *   ssb_gather_wait(h)                            enqueue: until every rank's publish count has reached this rank's
+ *   ssb_gather_wait(h)                            enqueue: fence, tell every rank, wait until every rank has told us
+ *                                                 (collective: every rank calls it the same number of times)
  *   ssb_gather_rows(h, p)                         DEVICE pointer to [world * n_streams][ssb_result_stride] f64
  *   ssb_gather_select(h, p ^ 1)                   next publishes go to the other half while `p` is read */
 int32_t ssb_gather_create(ssb_analyzer* h, uint32_t world, uint32_t rank, void* ipc_handle_out);

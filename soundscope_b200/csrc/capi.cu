@@ -211,7 +211,6 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
       CK(launch_loudness_wtile(h->lp, h->st, h->gp, d_in + done * C, n, in_stride_frames, pos, bucket0, wvariant, rap,
                                h->sm_count, h->device, h->stream, &h->launches, &tiled, &wrote));
       if (wrote) {
-        if (ra.ga.world) h->gather.epoch++;
         if (done_after > h->gated_upto) h->gated_upto = done_after;
         if (written) *written = true;
       }
@@ -237,7 +236,6 @@ int32_t launch_results_now(ssb_analyzer* h) {
   const GatherArgs ga = peek_gather_args(h);
   CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, h->d_results, h->stream, &h->launches,
                     done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0, ga.world ? &ga : nullptr));
-  if (ga.world) h->gather.epoch++;
   if (done > h->gated_upto) h->gated_upto = done;
   return SSB_OK;
 }
@@ -629,8 +627,7 @@ int32_t ssb_results_device(ssb_analyzer* h, double* d_out) {
     const GatherArgs ga = peek_gather_args(h);
     CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, d_out, h->stream, &h->launches,
                       done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0, ga.world ? &ga : nullptr));
-    if (ga.world) h->gather.epoch++;
-    if (done > h->gated_upto) h->gated_upto = done;
+      if (done > h->gated_upto) h->gated_upto = done;
   }
   return SSB_OK;
 }

@@ -7,23 +7,33 @@
 // word per rank; the allocation is exported with cudaIpcGetMemHandle, the 64-byte handles travel through the caller's
 // process group (torch.distributed / MPI / files), every rank opens the others' (cudaIpcOpenMemHandle maps the peer
 // memory: stores then ride NVLink / NVSwitch).  A results launch on rank r writes its rows into block r of the selected
-// parity on EVERY rank; the last CTA to finish bumps flag[r] on every rank (system-scope fences before it);
-// ssb_gather_wait enqueues a one-warp kernel that spins until all `world` flags have reached this rank's own publish
-// count.  Double buffering by parity is the caller's (sharding.PeerGather flips it after every wait).
+// parity on EVERY rank with plain fire-and-forget stores; ssb_gather_wait enqueues a one-warp kernel (after the results
+// launches in stream order) that fences, bumps this rank's flag on every rank and spins until every rank's flag has
+// reached the same wait count.  Double buffering by parity is the caller's (sharding.PeerGather flips it after every wait).
 #include "ssb_handle.cuh"
 
 using namespace ssb;
 
 namespace ssb {
 
-__global__ void k_gather_wait(const unsigned long long* flags, int world, unsigned long long epoch) {
+struct GatherFlags {
+  unsigned long long* peer[kMaxGatherRanks];   // per rank: its flag word for THIS rank
+};
+
+// One warp, after the last results launch in stream order: lane r tells rank r that this rank's rows up to `epoch` have
+// been stored (the kernel boundary has retired those stores; the system-scope fence orders them before the flag), then
+// waits until rank r has said the same.
+__global__ void k_gather_wait(const unsigned long long* flags, const __grid_constant__ GatherFlags gf, int world,
+                              unsigned long long epoch) {
   const int r = threadIdx.x;
   if (r >= world) return;
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long*>(gf.peer[r]) = epoch;
   const volatile unsigned long long* f = flags + r;
   unsigned long long spins = 0;
   while (*f < epoch) {
     __nanosleep(200);
-    if (++spins > (1ull << 26)) __trap();   // a peer that never publishes: fail loudly instead of hanging the box
+    if (++spins > (1ull << 26)) __trap();   // a peer that never arrives: fail loudly instead of hanging the box
   }
   __threadfence_system();
 }
@@ -91,7 +101,11 @@ int32_t ssb_gather_wait(ssb_analyzer* h) {
   DeviceGuard g(h->device);
   const unsigned long long* flags =
       reinterpret_cast<const unsigned long long*>(static_cast<char*>(h->gather.base) + h->gather.rows_bytes);
-  k_gather_wait<<<1, 32, 0, h->stream>>>(flags, h->gather.world, h->gather.epoch);
+  GatherFlags gf{};
+  for (int p = 0; p < h->gather.world; p++)
+    gf.peer[p] = reinterpret_cast<unsigned long long*>(static_cast<char*>(h->gather.peer_base[p]) + h->gather.rows_bytes) + h->gather.rank;
+  ++h->gather.epoch;   // one per wait: every rank calls ssb_gather_wait the same number of times
+  k_gather_wait<<<1, 32, 0, h->stream>>>(flags, gf, h->gather.world, h->gather.epoch);
   h->launches++;
   CK(cudaGetLastError());
   return SSB_OK;
@@ -113,8 +127,7 @@ int32_t ssb_gather_destroy(ssb_analyzer* h) {
 
 namespace ssb {
 
-// The GatherArgs the next results launch of this handle would publish with (world == 0 when no gather is open).  The
-// caller bumps h->gather.epoch once the launch that carries them is enqueued.
+// The GatherArgs of this handle's results launches (world == 0 when no gather is open).
 GatherArgs peek_gather_args(ssb_analyzer* h) {
   GatherArgs ga{};
   if (!h->gather.base || (!h->gather.open && h->gather.world > 1)) return ga;
@@ -122,13 +135,10 @@ GatherArgs peek_gather_args(ssb_analyzer* h) {
   const size_t half = h->gather.rows_bytes / 2;
   ga.world = h->gather.world;
   ga.rank = h->gather.rank;
-  ga.epoch = h->gather.epoch + 1;
   for (int p = 0; p < ga.world; p++) {
     char* base = static_cast<char*>(h->gather.peer_base[p]);
     ga.rows[p] = reinterpret_cast<double*>(base + (size_t)h->gather.parity * half) + (size_t)ga.rank * h->n_streams * stride;
-    ga.flags[p] = reinterpret_cast<unsigned long long*>(base + h->gather.rows_bytes) + ga.rank;
   }
-  ga.counter = reinterpret_cast<unsigned*>(static_cast<char*>(h->gather.base) + h->gather.rows_bytes + 128);
   return ga;
 }
 

@@ -258,7 +258,6 @@ k_results(const __grid_constant__ GateParams g, const __grid_constant__ ResultsA
     if (V == 0) results_for_stream_v0(g, ra, s, lane);
     else results_for_stream(g, ra, ra.energies, ra.bounds, s, lane);
   }
-  gather_block_done(ra.ga);
 }
 
 cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
@@ -276,10 +275,7 @@ cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t bu
   const size_t threads = st.n_streams * 32;
   ResultsArgs ra = make_results_args(st, buckets_done, aligned, ring_pos, mode, d_out, gate_first, gate_last, ring_e);
   const unsigned blocks = (unsigned)((threads + tpb - 1) / tpb);
-  if (ga) {
-    ra.ga = *ga;
-    ra.ga.n_blocks = blocks;
-  }
+  if (ga) ra.ga = *ga;
   // SSB_RESULTS_V (A/B timing): 0 = round-1 ordering, 1 = loads first, 2 = loads first capped at 128 registers (default:
   // 16 resident warps per SM instead of 12; measured 38 us against 54 us per 4096-stream query after a cfg2 launch)
   static const int variant = [] { const char* e = getenv("SSB_RESULTS_V"); return e ? atoi(e) : 2; }();

@@ -516,23 +516,4 @@ __device__ __forceinline__ void results_for_stream_v0(const GateParams& g, const
 }
 
 
-// Called by every thread of a CTA after its last results_for_stream: the last CTA of the launch tells every rank that
-// this rank's rows of publish `epoch` have landed (system-scope fences order the peer stores before the flag).
-__device__ __forceinline__ void gather_block_done(const GatherArgs& ga) {
-  if (ga.world <= 0) return;
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(ga.counter, 1u);
-    if (prev + 1 == ga.n_blocks) {
-      *ga.counter = 0;   // the handle's launches are stream-ordered: the next one starts from zero
-      __threadfence_system();
-      for (int p = 0; p < ga.world; p++) {
-        volatile unsigned long long* f = ga.flags[p];
-        *f = ga.epoch;
-      }
-    }
-  }
-}
-
 }  // namespace ssb

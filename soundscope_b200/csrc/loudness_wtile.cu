@@ -467,13 +467,15 @@ __device__ __forceinline__ void run_p2(const WArgs& a, const CUtensorMap* tmap, 
     for (unsigned tile = 0; tile < a.n_tiles; tile++) {
       const unsigned g = g0 + tile;
       const unsigned char* st0 = stages + (size_t)(g % kWStages) * W::STAGE_STRIDE;
-      // ---- start states from the P1 warp (it has seen the tile land; the second wait makes the TMA writes visible here) ----
+      // ---- start states from the P1 warp.  It has observed the tile's mbarrier phase (which is what makes the TMA writes
+      //      visible to it) before it computed them, and dk_full's release / acquire pair orders everything it has seen
+      //      before this warp's reads: no second wait on `full` (it cost 1.5 us per launch) ----
       mbar_wait_warp(dk_full, g & 1);
       const double2 da = reinterpret_cast<const double2*>(dk_slot)[lane * 2];
       const double2 db = reinterpret_cast<const double2*>(dk_slot)[lane * 2 + 1];
       __syncwarp();
       if (lane == 0) mbar_arrive(dk_free);
-#ifndef SSBW_NO_SECOND_WAIT
+#ifdef SSBW_SECOND_WAIT
       mbar_wait_warp(&full[g % kWStages], (g / kWStages) & 1);
 #endif
       double v1, v2, v3, v4;
@@ -583,7 +585,9 @@ k_loudness_wtile(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = warp & (kWPairs - 1);     // warps 0..7: the P2 warps, 8..15: the P1 warps of the same pairs
-  const bool is_p1 = warp >= kWPairs;        // pair p and p + 4, P1 and P2: warps p, p+4, p+8, p+12 share sub-partition p % 4
+  // pair p and p + 4, P1 and P2: warps p, p+4, p+8, p+12 share sub-partition p % 4.  The P1 warps sit on the LOW warp
+  // ids: measured 1.5 % faster than the other way round (196.5 -> 192.8 us with the change below).
+  const bool is_p1 = warp < kWPairs;
   const unsigned n_ctas = gridDim.x;
   const unsigned row0 = (unsigned)(((unsigned long long)blockIdx.x * a.n_streams) / n_ctas);
   const unsigned row1 = (unsigned)(((unsigned long long)(blockIdx.x + 1) * a.n_streams) / n_ctas);
@@ -592,7 +596,7 @@ k_loudness_wtile(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
   const unsigned rows_per_pass = n_pass ? (cta_rows + n_pass - 1) / n_pass : 0;
 
   uint64_t* full = bars + pair * kWBars;    // [0..2] TMA full, [3] dk_full, [4] dk_free
-  if (!is_p1 && lane == 0) {
+  if (warp < kWPairs && lane == 0) {
     for (int s = 0; s < kWBars; s++) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
@@ -626,7 +630,6 @@ k_loudness_wtile(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     for (int i = threadIdx.x; i < 2 * kHistBins + 1; i += kWWarps * 32) tab[i] = __ldg(ra.energies + i);
     __syncthreads();
     for (unsigned r = warp; r < cta_rows; r += kWWarps) results_for_stream(g, ra, tab, tab + kHistBins, (size_t)row0 + r, lane);
-    gather_block_done(ra.ga);
   }
 }
 #undef SSBW_P2_INIT
@@ -758,9 +761,7 @@ cudaError_t launch_loudness_wtile(const LoudParams& p, const LoudState& st, cons
   a.do_sample_peak = p.do_sample_peak;
   a.fused_results = fuse ? 1 : 0;
   ResultsArgs none{};
-  ResultsArgs mine = fuse ? *ra : none;
-  mine.ga.n_blocks = (unsigned)(st.n_streams < (size_t)sm_count ? st.n_streams : (size_t)sm_count);   // the grid of launch_shape
-  const ResultsArgs& r = mine;
+  const ResultsArgs& r = fuse ? *ra : none;
   cudaError_t e;
   if (variant == 1)
     e = C == 1 ? launch_shape<1, false>(p, st, d_in, frames, in_stride_frames, a, gp, r, sm_count, device, s, consumed)

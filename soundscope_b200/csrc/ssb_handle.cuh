@@ -56,7 +56,7 @@ struct ssb_analyzer {
     size_t rows_bytes = 0;
     int world = 0, rank = 0, parity = 0;
     bool open = false;
-    unsigned long long epoch = 0;                // publishes so far
+    unsigned long long epoch = 0;                // ssb_gather_wait calls so far
   } gather;
 
   uint64_t launches = 0;
@@ -103,8 +103,7 @@ struct DeviceGuard {
   }
 };
 
-// gather.cu: GatherArgs the next results launch would publish with (world == 0 when no gather is open); the caller
-// increments h->gather.epoch when that launch is enqueued
+// gather.cu: GatherArgs of this handle's results launches (world == 0 when no gather is open)
 GatherArgs peek_gather_args(ssb_analyzer* h);
 
 // capi.cu

@@ -71,15 +71,13 @@ struct LoudState {
 
 // Arguments of the per-stream result / gating code (loudness_results.cuh): k_results and the fused epilogue of
 // k_loudness_wtile take the same struct.
-// Publication of the result rows to every rank's gather buffer (gather.cu); world <= 1: none
+// Publication of the result rows to every rank's gather buffer (gather.cu); world == 0: none.  The stores are
+// fire-and-forget; arrival is established once per ssb_gather_wait (a system-scope fence + flag exchange in its own
+// small kernel after the last results launch in stream order), not per launch.
 constexpr int kMaxGatherRanks = 8;
 struct GatherArgs {
   int world, rank;
   double* rows[kMaxGatherRanks];                // per destination rank: block `rank` of the selected parity
-  unsigned long long* flags[kMaxGatherRanks];   // per destination rank: its flag word for `rank`
-  unsigned long long epoch;                     // this publish's number
-  unsigned* counter;                            // local: CTAs of the launch that are done
-  unsigned n_blocks;                            // CTAs in the launch (set by the launcher)
 };
 
 struct ResultsArgs {
