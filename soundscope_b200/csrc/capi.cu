@@ -21,6 +21,7 @@ namespace {
 void free_meter(ssb_analyzer* h) {
   cudaFree(h->st.filt); cudaFree(h->st.bucket); cudaFree(h->st.block_hist); cudaFree(h->st.st_hist);
   cudaFree(h->st.speak); cudaFree(h->st.tpeak); cudaFree(h->st.tphist); cudaFree(h->st.ring); cudaFree(h->st.ring_e);
+  cudaFree(h->st.cache);
   cudaFree(h->d_results);
   cudaFree(h->d_scan_powers);
   h->d_scan_powers = nullptr;
@@ -76,6 +77,7 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
   CK(cudaMalloc(&st.speak, chains * sizeof(float)));
   CK(cudaMalloc(&st.tpeak, chains * sizeof(float)));
   CK(cudaMalloc(&st.tphist, chains * kTpHist * sizeof(float)));
+  CK(cudaMalloc(&st.cache, n * sizeof(StreamCache)));
   st.ring = nullptr;
   st.ring_e = nullptr;
   st.ring_frames = 0;
@@ -99,6 +101,11 @@ int32_t init_meter(ssb_analyzer* h, uint32_t channels, uint32_t rate) {
   h->results_valid = false;
   h->dres_valid = false;
   CK(launch_reset(st, (int)channels, h->stream, &h->launches));
+  h->lra_cache_valid = h->icache_valid = true;   // zeroed by the reset: the cache of an empty meter
+  {
+    const char* e = getenv("SSB_RESULTS_LEAN");   // A/B switch: 0 = always the full histogram scan
+    h->lean_enabled = !(e && atoi(e) == 0);
+  }
   h->meter_ok = true;
   return SSB_OK;
 }
@@ -147,8 +154,40 @@ static int32_t flush_gating(ssb_analyzer* h) {
   if (done > h->gated_upto) {
     CK(launch_gating(h->gp, h->st, h->gated_upto, done - 1, h->stream, &h->launches));
     h->gated_upto = done;
+    h->lra_cache_valid = h->icache_valid = false;   // k_gating enters blocks / short-term energies behind the cache's back
   }
   return SSB_OK;
+}
+
+// What the results code of one launch may take from the per-stream cache (StreamCache), and the cache's state after it.
+//  * loudness range: the short-term histogram only changes when a 3 s entry is gated (bucket j with j >= 29 and
+//    (j - 29) % 10 == 0, once per second of audio), so a launch scans it only then, or when the cache is stale;
+//  * integrated loudness: the lean path patches the cached gating sums with the pending blocks; it needs a current
+//    cache, the bucket-based momentary / short-term windows (no ring), few pending buckets and few channels.  Every
+//    full scan rebuilds the cache, so one non-lean launch makes the next ones lean again.
+struct ResultsMode {
+  int lra_from_cache, lean;
+  bool lra_valid_before, i_valid_before;
+};
+static ResultsMode results_mode_for_launch(ssb_analyzer* h, uint64_t gate_first, uint64_t gate_last) {
+  ResultsMode m;
+  m.lra_valid_before = h->lra_cache_valid;
+  m.i_valid_before = h->icache_valid;
+  bool st_entry = false;
+  for (uint64_t j = gate_first; j <= gate_last && gate_last >= gate_first; j++)
+    if (j >= 29 && (j - 29) % 10 == 0) { st_entry = true; break; }
+  const uint64_t n_pending = gate_last >= gate_first ? gate_last - gate_first + 1 : 0;
+  const bool want_i = (h->mode & SSB_MODE_I) == SSB_MODE_I, want_lra = (h->mode & SSB_MODE_LRA) == SSB_MODE_LRA;
+  m.lra_from_cache = (h->lra_cache_valid && !st_entry) ? 1 : 0;
+  m.lean = (h->lean_enabled && h->icache_valid && want_i && !h->st.ring && h->channels <= (uint32_t)kLeanMaxChannels &&
+            n_pending <= (uint64_t)kLeanPending) ? 1 : 0;
+  if (want_lra) h->lra_cache_valid = true;
+  if (want_i) h->icache_valid = true;
+  return m;
+}
+static void restore_results_mode(ssb_analyzer* h, const ResultsMode& m) {
+  h->lra_cache_valid = m.lra_valid_before;
+  h->icache_valid = m.i_valid_before;
 }
 
 // feed `frames` frames per stream from device memory laid out [stream][in_stride_frames][C]
@@ -198,6 +237,7 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
       // results fused into the filter launch when the caller wants them and this launch ends the feed on whole tiles
       ResultsArgs ra{};
       const ResultsArgs* rap = nullptr;
+      ResultsMode rm{};
       const uint64_t frames_after = h->total_frames + n;
       const uint64_t done_after = frames_after / s100;
       if (d_results && last_chunk) {
@@ -206,13 +246,19 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
                                pending ? h->gated_upto : 1, pending ? done_after - 1 : 0, nullptr);
         ra.ga = peek_gather_args(h);   // rows also go to every rank's gather buffer when one is open
         rap = &ra;
+        rm = results_mode_for_launch(h, pending ? h->gated_upto : 1, pending ? done_after - 1 : 0);
+        ra.lra_from_cache = rm.lra_from_cache;
+        ra.lean = rm.lean;
       }
       bool wrote = false;
+      // (if the launch turns out not to write the rows, the cache flag goes back to what it was)
       CK(launch_loudness_wtile(h->lp, h->st, h->gp, d_in + done * C, n, in_stride_frames, pos, bucket0, wvariant, rap,
                                h->sm_count, h->device, h->stream, &h->launches, &tiled, &wrote));
       if (wrote) {
         if (done_after > h->gated_upto) h->gated_upto = done_after;
         if (written) *written = true;
+      } else if (rap) {
+        restore_results_mode(h, rm);
       }
     } else if (fk != 1 && fk != 4 && fk != 5 && fk != 6 && tile_path_usable(h->lp, h->st, d_in + done * C, n, in_stride_frames))
       CK(launch_loudness_tile(h->lp, h->st, d_in + done * C, n, in_stride_frames, pos, bucket0, h->stream,
@@ -234,8 +280,10 @@ int32_t launch_results_now(ssb_analyzer* h) {
   const int aligned = (h->total_frames % h->lp.s100) == 0;
   const uint64_t done = h->total_frames / h->lp.s100;
   const GatherArgs ga = peek_gather_args(h);
-  CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, h->d_results, h->stream, &h->launches,
-                    done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0, ga.world ? &ga : nullptr));
+  const uint64_t gf = done > h->gated_upto ? h->gated_upto : 1, gl = done > h->gated_upto ? done - 1 : 0;
+  const ResultsMode rm = results_mode_for_launch(h, gf, gl);
+  CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, h->d_results, h->stream, &h->launches, gf, gl,
+                    ga.world ? &ga : nullptr, rm.lra_from_cache, rm.lean));
   if (done > h->gated_upto) h->gated_upto = done;
   return SSB_OK;
 }
@@ -530,6 +578,7 @@ int32_t ssb_reset(ssb_analyzer* h) {
   h->ring_pos = 0;
   h->results_valid = false;
   h->dres_valid = false;
+  h->lra_cache_valid = h->icache_valid = true;   // zeroed by launch_reset
   return SSB_OK;
 }
 
@@ -625,8 +674,10 @@ int32_t ssb_results_device(ssb_analyzer* h, double* d_out) {
   {
     const uint64_t done = h->total_frames / h->lp.s100;
     const GatherArgs ga = peek_gather_args(h);
-    CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, d_out, h->stream, &h->launches,
-                      done > h->gated_upto ? h->gated_upto : 1, done > h->gated_upto ? done - 1 : 0, ga.world ? &ga : nullptr));
+    const uint64_t gf = done > h->gated_upto ? h->gated_upto : 1, gl = done > h->gated_upto ? done - 1 : 0;
+    const ResultsMode rm = results_mode_for_launch(h, gf, gl);
+    CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, d_out, h->stream, &h->launches, gf, gl,
+                      ga.world ? &ga : nullptr, rm.lra_from_cache, rm.lean));
       if (done > h->gated_upto) h->gated_upto = done;
   }
   return SSB_OK;
@@ -695,6 +746,7 @@ static int32_t one_shot_integrated(ssb_analyzer* h, uint32_t channels, const flo
       if (!e) e = launch_file_gating(tmp->gp, tmp->st, d_fb, stride, n_buckets, tmp->stream, &tmp->launches);
       if (e) return cuda_fail(h, e, "calculate_integrated_lufs (file path)");
       tmp->results_valid = false;   // total_frames stays 0: nothing is pending for the streaming gating
+      tmp->lra_cache_valid = tmp->icache_valid = false;
     } else {
       for (size_t off = 0; off < len && !rc; off += chunk) {
         const size_t n = len - off < chunk ? len - off : chunk;

@@ -80,8 +80,13 @@ int truepeak_taps(uint32_t rate, float tp4[3][12], float tp2[24], int force_fact
   return factor;
 }
 
+double histogram_bound0() {
+  static const double b0 = pow(10.0, (-70.0 + 0.691) / 10.0);
+  return b0;
+}
+
 void histogram_tables(double energies[1000], double boundaries[1001]) {
-  boundaries[0] = pow(10.0, (-70.0 + 0.691) / 10.0);
+  boundaries[0] = histogram_bound0();
   for (int i = 0; i < 1000; i++) energies[i] = pow(10.0, ((double)i / 10.0 - 69.95 + 0.691) / 10.0);
   for (int i = 1; i < 1001; i++) boundaries[i] = pow(10.0, ((double)i / 10.0 - 70.0 + 0.691) / 10.0);
 }

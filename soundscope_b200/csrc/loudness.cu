@@ -249,20 +249,35 @@ k_ring_energy(const GateParams g, const double* __restrict__ ring, size_t ring_f
   }
 }
 
-template <int V>
-__global__ void __launch_bounds__(128, V == 2 ? 4 : 1)
+// 128 registers per thread: 16 resident warps per SM instead of 12 (measured 38 us against 54 us per 4096-stream query
+// after a cfg2 launch)
+__global__ void __launch_bounds__(128, 4)
 k_results(const __grid_constant__ GateParams g, const __grid_constant__ ResultsArgs ra, size_t n_streams) {
   const size_t s = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (s < n_streams) {
-    if (V == 0) results_for_stream_v0(g, ra, s, lane);
-    else results_for_stream(g, ra, ra.energies, ra.bounds, s, lane);
+  if (s < n_streams) results_for_stream<R_ALL>(g, ra, ra.energies, ra.bounds, s, lane);
+}
+
+// The lean path (loudness_results.cuh): two streams per warp, eight per CTA; the launches that gate a 3 s entry finish
+// each stream's row with the short-term histogram scan.
+__global__ void __launch_bounds__(128)
+k_results_lean(const __grid_constant__ GateParams g, const __grid_constant__ ResultsArgs ra, size_t n_streams) {
+  __shared__ double stg[4][2][kLeanSlots * kLeanMaxChannels];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t s0 = ((size_t)blockIdx.x * 4 + warp) * 2;
+  const size_t s = s0 + (lane >> 4);
+  const bool valid = s < n_streams;
+  const bool lra_scan = (ra.mode & SSB_MODE_LRA) == SSB_MODE_LRA && !ra.lra_from_cache;
+  results_lean(g, ra, stg[warp][lane >> 4], valid ? s : 0, valid, lane, !lra_scan);
+  if (lra_scan) {
+    for (int q = 0; q < 2; q++)
+      if (s0 + q < n_streams) results_for_stream<R_LRA | R_GATHER>(g, ra, ra.energies, ra.bounds, s0 + q, lane);
   }
 }
 
 cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
                            size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches,
-                           uint64_t gate_first, uint64_t gate_last, const GatherArgs* ga) {
+                           uint64_t gate_first, uint64_t gate_last, const GatherArgs* ga, int lra_from_cache, int lean) {
   if (!st.n_streams) return cudaSuccess;
   const double* ring_e = nullptr;
   if (st.ring && st.ring_e) {
@@ -272,16 +287,16 @@ cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t bu
     ring_e = st.ring_e;
   }
   const int tpb = 128;
-  const size_t threads = st.n_streams * 32;
   ResultsArgs ra = make_results_args(st, buckets_done, aligned, ring_pos, mode, d_out, gate_first, gate_last, ring_e);
-  const unsigned blocks = (unsigned)((threads + tpb - 1) / tpb);
   if (ga) ra.ga = *ga;
-  // SSB_RESULTS_V (A/B timing): 0 = round-1 ordering, 1 = loads first, 2 = loads first capped at 128 registers (default:
-  // 16 resident warps per SM instead of 12; measured 38 us against 54 us per 4096-stream query after a cfg2 launch)
-  static const int variant = [] { const char* e = getenv("SSB_RESULTS_V"); return e ? atoi(e) : 2; }();
-  if (variant == 0) k_results<0><<<blocks, tpb, 0, s>>>(g, ra, st.n_streams);
-  else if (variant == 2) k_results<2><<<blocks, tpb, 0, s>>>(g, ra, st.n_streams);
-  else k_results<1><<<blocks, tpb, 0, s>>>(g, ra, st.n_streams);
+  ra.lra_from_cache = lra_from_cache;
+  ra.lean = (lean && !st.ring && g.channels <= kLeanMaxChannels) ? 1 : 0;
+  if (ra.lean) {
+    k_results_lean<<<(unsigned)((st.n_streams + 7) / 8), tpb, 0, s>>>(g, ra, st.n_streams);
+  } else {
+    const size_t threads = st.n_streams * 32;
+    k_results<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, s>>>(g, ra, st.n_streams);
+  }
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -308,6 +323,7 @@ cudaError_t launch_reset(const LoudState& st, int channels, cudaStream_t s, uint
   if ((e = cudaMemsetAsync(st.speak, 0, chains * sizeof(float), s))) return e;
   if ((e = cudaMemsetAsync(st.tpeak, 0, chains * sizeof(float), s))) return e;
   if ((e = cudaMemsetAsync(st.tphist, 0, chains * kTpHist * sizeof(float), s))) return e;
+  if (st.cache && (e = cudaMemsetAsync(st.cache, 0, st.n_streams * sizeof(StreamCache), s))) return e;
   if (st.ring && (e = cudaMemsetAsync(st.ring, 0, st.n_streams * st.ring_frames * channels * sizeof(double), s))) return e;
   (void)launches;
   return cudaSuccess;

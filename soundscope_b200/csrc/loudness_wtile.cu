@@ -621,15 +621,53 @@ k_loudness_wtile(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
       else run_p2<WB>(a, &tmapB, stages, full, full + 3, full + 4, dk_slot, gm, lane);
     }
   }
-  if (a.fused_results) {
-    // gating + result rows of this CTA's streams (analyzer.rs:147-164), one warp per stream; the bucket sums and peaks
-    // written above by other warps of this CTA are visible after the barrier
+  if (a.fused_results && ra.lean) {
+    // gating + result rows (analyzer.rs:147-164), lean form: the two warps of a pair meet on their own named barrier as
+    // soon as the pair's last tile is done and split the pair's streams, two per warp at a time (16 lanes each); the
+    // pairs that finish early (the lighter type-B sets) do this while the others still filter.  No CTA-wide barrier.
+    if (cta_rows) {
+      PairGeom gm;
+      gm.cta_row0 = row0;
+      gm.cta_rows = cta_rows;
+      gm.rows_per_pass = rows_per_pass;
+      gm.n_pass = n_pass;
+      const unsigned R = pair < 4 ? (unsigned)WA::R : (unsigned)WB::R;
+      gm.warp_off = pair < 4 ? (unsigned)pair * WA::R : 4u * WA::R + (unsigned)(pair - 4) * WB::R;
+      unsigned char* stages = pair < 4 ? smem + (size_t)pair * kWStages * WA::STAGE_STRIDE
+                                       : smem + (size_t)4 * kWStages * WA::STAGE_STRIDE + (size_t)(pair - 4) * kWStages * WB::STAGE_STRIDE;
+      const unsigned n_task = count_tasks<WA>(gm);
+      if (n_task) {
+        // the bucket sums (P2 warp) and peaks (P1 warp) of the pair's streams are visible to both warps after this
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+        double* stg = reinterpret_cast<double*>(stages) + ((is_p1 ? 2 : 0) + (lane >> 4)) * (kLeanSlots * C);
+        const bool lra_scan = (ra.mode & SSB_MODE_LRA) == SSB_MODE_LRA && !ra.lra_from_cache;
+        for (unsigned task = 0; task < n_task; task++) {
+          const unsigned rp = min(rows_per_pass, cta_rows - task * rows_per_pass);
+          const unsigned nrows = min(R, rp - gm.warp_off);
+          const size_t row_g = (size_t)row0 + task * rows_per_pass + gm.warp_off;
+          for (unsigned item = (task + (is_p1 ? 1u : 0u)) & 1u; item * 2 < nrows; item += 2) {
+            const unsigned r = item * 2 + (unsigned)(lane >> 4);
+            const bool valid = r < nrows;
+            __syncwarp();   // the previous item's reads of the staging slots are done
+            results_lean(g, ra, stg, row_g + (valid ? r : 0), valid, lane, !lra_scan);
+            if (lra_scan) {
+              for (unsigned q = 0; q < 2; q++)
+                if (item * 2 + q < nrows)
+                  results_for_stream<R_LRA | R_GATHER>(g, ra, ra.energies, ra.bounds, row_g + item * 2 + q, lane);
+            }
+          }
+        }
+      }
+    }
+  } else if (a.fused_results) {
+    // the full form (stale cache, many pending buckets): one warp per stream after a CTA-wide barrier; the bucket sums
+    // and peaks written above by other warps of this CTA are visible after the barrier
     __syncthreads();
     // the histogram tables (energies[1000] | boundaries[1001], contiguous) into the now idle stage memory
     double* tab = reinterpret_cast<double*>(smem);
     for (int i = threadIdx.x; i < 2 * kHistBins + 1; i += kWWarps * 32) tab[i] = __ldg(ra.energies + i);
     __syncthreads();
-    for (unsigned r = warp; r < cta_rows; r += kWWarps) results_for_stream(g, ra, tab, tab + kHistBins, (size_t)row0 + r, lane);
+    for (unsigned r = warp; r < cta_rows; r += kWWarps) results_for_stream<R_ALL>(g, ra, tab, tab + kHistBins, (size_t)row0 + r, lane);
   }
 }
 #undef SSBW_P2_INIT

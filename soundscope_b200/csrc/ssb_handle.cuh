@@ -33,6 +33,9 @@ struct ssb_analyzer {
   double* d_results = nullptr;
   double* h_results = nullptr;  // pinned
   bool results_valid = false;
+  bool lra_cache_valid = false; // st.cache[].lra is every stream's LRA for the current short-term histograms
+  bool icache_valid = false;    // st.cache[]'s gating sums match the block histograms (StreamCache)
+  bool lean_enabled = true;     // SSB_RESULTS_LEAN=0 at create: always the full histogram scan (A/B, tests)
   bool dres_valid = false;      // d_results already holds the rows for the current feed position (fused epilogue)
   bool meter_ok = false;        // false while (re)initialisation failed half-way: every meter call then fails loudly
 

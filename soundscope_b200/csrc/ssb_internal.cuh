@@ -47,10 +47,28 @@ void kweight_coeffs(uint32_t rate, double b[5], double a[5]);
 void default_channel_weights(uint32_t channels, float w[kMaxChannels], uint64_t* active_mask);
 int truepeak_taps(uint32_t rate, float tp4[3][12], float tp2[24], int force_factor = 0);   // returns factor 0/2/4
 void histogram_tables(double energies[1000], double boundaries[1001]);
+double histogram_bound0();                                           // boundaries[0]
 float libm_cosf(float x);                                            // libm 0.2.16 (musl) cosf
 void hann_multipliers(size_t n, std::vector<float>& w);             // spectrum-analyzer hann_window
 size_t fft_bin_range(size_t n, uint32_t rate, size_t* k_first);
 void fft_axis(size_t n, uint32_t rate, std::vector<double>& x, std::vector<double>& tilt, size_t* k_first);
+
+// Per-stream running sums of the histogram gating (one 64-byte line per stream).  ebur128's gated_loudness walks the
+// 1000-bin block histogram twice per query; between two queries only the newly gated blocks change it, so the lean
+// results path (loudness_results.cuh: results_lean) keeps what the walk computes and patches it: the count and energy
+// sum of every block above the absolute gate, the relative gate's start bin for those sums, and the count and energy
+// sum of the bins from `start` up.  `lra` is the loudness range as of the last short-term histogram change.  A full
+// scan (results_for_stream) rewrites all of it; the host tracks validity per handle (ssb_analyzer::icache_valid /
+// lra_cache_valid).  All zero is the correct cache of an empty meter.
+struct alignas(64) StreamCache {
+  unsigned long long n_all;
+  double sum_all;
+  unsigned long long n_above;
+  double sum_above;
+  long long start;
+  double lra;
+  double pad[2];
+};
 
 // --- kernel launchers (loudness.cu) ------------------------------------------------------------
 struct LoudState {
@@ -65,6 +83,7 @@ struct LoudState {
   double* ring;       // [n][ring_frames][C] or nullptr
   size_t ring_frames;
   double* ring_e;     // [n][2] scratch: momentary / short-term energies from the ring
+  StreamCache* cache; // [n] running gating sums + loudness range (see StreamCache)
   const double* hist_energies;    // [1000]
   const double* hist_boundaries;  // [1001]
 };
@@ -98,7 +117,19 @@ struct ResultsArgs {
   double* out;                   // [n][4 + 2C]
   uint64_t gate_first, gate_last;  // buckets to enter into the histograms first (none when gate_last < gate_first)
   GatherArgs ga;                   // zero unless a gather is open on the handle
+  // The short-term histogram only changes when a 3 s entry is gated (once per second of audio), so the loudness range
+  // is kept per stream: lra_from_cache != 0 -> read it instead of loading and scanning the 1000 bins again.  The caller
+  // sets it only when no pending bucket of this call is a short-term entry and the cache is current.
+  StreamCache* cache;
+  int lra_from_cache;
+  // lean != 0: the block-histogram sums in `cache` are current and at most kLeanPending buckets are pending, so the
+  // integrated loudness is patched instead of re-scanned (results_lean: 16 lanes per stream).
+  int lean;
+  double bound0;                   // boundaries[0]: the absolute gate (-70 LUFS) as an energy
 };
+constexpr int kLeanPending = 10;   // pending buckets a lean call can gate (one lane each; at most one 3 s entry among them)
+constexpr int kLeanSlots = 40;     // buckets per channel a lean call looks back over (3 s window of the oldest pending entry)
+constexpr int kLeanMaxChannels = 6;   // 4 + 2 C result values fit the 16 lanes of a stream
 
 inline ResultsArgs make_results_args(const LoudState& st, uint64_t buckets_done, int aligned, size_t ring_pos, int mode,
                                      double* d_out, uint64_t gate_first, uint64_t gate_last, const double* ring_e) {
@@ -122,6 +153,10 @@ inline ResultsArgs make_results_args(const LoudState& st, uint64_t buckets_done,
   ra.out = d_out;
   ra.gate_first = gate_first;
   ra.gate_last = gate_last;
+  ra.cache = st.cache;
+  ra.lra_from_cache = 0;
+  ra.lean = 0;
+  ra.bound0 = histogram_bound0();
   return ra;
 }
 
@@ -177,7 +212,8 @@ cudaError_t launch_gating(const GateParams& g, const LoudState& st, uint64_t j_f
 // [gate_first, gate_last] (none when gate_last < gate_first) are gated inside the same launch first.
 cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
                            size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches,
-                           uint64_t gate_first, uint64_t gate_last, const GatherArgs* ga = nullptr);
+                           uint64_t gate_first, uint64_t gate_last, const GatherArgs* ga = nullptr, int lra_from_cache = 0,
+                           int lean = 0);
 cudaError_t launch_reset(const LoudState& st, int channels, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_histogram_index(const LoudState& st, const double* d_e, size_t n, int32_t* d_out, cudaStream_t s);
 
