@@ -435,7 +435,7 @@ def test_default_dispatch_at_scale_matches_oracle_subset(ssb, oracle, cuda, n, c
     b = ssb.BatchAnalyzer(n, channels, rate, mode)          # no force_kernel: automatic dispatch
     sub = np.unique(np.concatenate([np.arange(0, n, n // 61), [n - 1, n - 2, 127, 128, 129]]))
     ob = oracle.Batch(len(sub), channels, rate, getattr(oracle, mode_name))
-    reps = 3
+    reps = max(3, -(-9 * rate // (10 * frames)))      # at least 0.9 s, so that 400 ms blocks exist
     for k in range(reps):
         x = bench.make_input_device_chunked(torch, n, frames, 900 + 31 * k, dev, chunk=2048, channels=channels, rate=rate)
         b.add_frames_device(x)
