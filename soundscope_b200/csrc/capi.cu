@@ -167,6 +167,7 @@ static int32_t flush_gating(ssb_analyzer* h) {
 //    full scan rebuilds the cache, so one non-lean launch makes the next ones lean again.
 struct ResultsMode {
   int lra_from_cache, lean;
+  int st_back;   // >= 0: the lean code gates the launch's 3 s entry itself and the loudness range comes from lra_scan_fast
   bool lra_valid_before, i_valid_before;
 };
 static ResultsMode results_mode_for_launch(ssb_analyzer* h, uint64_t gate_first, uint64_t gate_last) {
@@ -174,13 +175,15 @@ static ResultsMode results_mode_for_launch(ssb_analyzer* h, uint64_t gate_first,
   m.lra_valid_before = h->lra_cache_valid;
   m.i_valid_before = h->icache_valid;
   bool st_entry = false;
+  uint64_t j_st = 0;
   for (uint64_t j = gate_first; j <= gate_last && gate_last >= gate_first; j++)
-    if (j >= 29 && (j - 29) % 10 == 0) { st_entry = true; break; }
+    if (j >= 29 && (j - 29) % 10 == 0) { st_entry = true; j_st = j; break; }
   const uint64_t n_pending = gate_last >= gate_first ? gate_last - gate_first + 1 : 0;
   const bool want_i = (h->mode & SSB_MODE_I) == SSB_MODE_I, want_lra = (h->mode & SSB_MODE_LRA) == SSB_MODE_LRA;
   m.lra_from_cache = (h->lra_cache_valid && !st_entry) ? 1 : 0;
   m.lean = (h->lean_enabled && h->icache_valid && want_i && !h->st.ring && h->channels <= (uint32_t)kLeanMaxChannels &&
             n_pending <= (uint64_t)kLeanPending) ? 1 : 0;
+  m.st_back = (m.lean && st_entry && want_lra && h->lra_cache_valid) ? (int)(gate_last - j_st) : -1;
   if (want_lra) h->lra_cache_valid = true;
   if (want_i) h->icache_valid = true;
   return m;
@@ -249,6 +252,8 @@ int32_t feed_device(ssb_analyzer* h, const float* d_in, size_t frames, size_t in
         rm = results_mode_for_launch(h, pending ? h->gated_upto : 1, pending ? done_after - 1 : 0);
         ra.lra_from_cache = rm.lra_from_cache;
         ra.lean = rm.lean;
+        ra.st_back = rm.st_back;
+        ra.lra_fast = rm.st_back >= 0 ? 1 : 0;
       }
       bool wrote = false;
       // (if the launch turns out not to write the rows, the cache flag goes back to what it was)
@@ -283,7 +288,7 @@ int32_t launch_results_now(ssb_analyzer* h) {
   const uint64_t gf = done > h->gated_upto ? h->gated_upto : 1, gl = done > h->gated_upto ? done - 1 : 0;
   const ResultsMode rm = results_mode_for_launch(h, gf, gl);
   CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, h->d_results, h->stream, &h->launches, gf, gl,
-                    ga.world ? &ga : nullptr, rm.lra_from_cache, rm.lean));
+                    ga.world ? &ga : nullptr, rm.lra_from_cache, rm.lean, rm.st_back));
   if (done > h->gated_upto) h->gated_upto = done;
   return SSB_OK;
 }
@@ -677,7 +682,7 @@ int32_t ssb_results_device(ssb_analyzer* h, double* d_out) {
     const uint64_t gf = done > h->gated_upto ? h->gated_upto : 1, gl = done > h->gated_upto ? done - 1 : 0;
     const ResultsMode rm = results_mode_for_launch(h, gf, gl);
     CK(launch_results(h->gp, h->st, done, aligned, h->ring_pos, h->mode, d_out, h->stream, &h->launches, gf, gl,
-                      ga.world ? &ga : nullptr, rm.lra_from_cache, rm.lean));
+                      ga.world ? &ga : nullptr, rm.lra_from_cache, rm.lean, rm.st_back));
       if (done > h->gated_upto) h->gated_upto = done;
   }
   return SSB_OK;

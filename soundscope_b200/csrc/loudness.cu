@@ -265,19 +265,13 @@ k_results_lean(const __grid_constant__ GateParams g, const __grid_constant__ Res
   __shared__ double stg[4][2][kLeanSlots * kLeanMaxChannels];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t s0 = ((size_t)blockIdx.x * 4 + warp) * 2;
-  const size_t s = s0 + (lane >> 4);
-  const bool valid = s < n_streams;
-  const bool lra_scan = (ra.mode & SSB_MODE_LRA) == SSB_MODE_LRA && !ra.lra_from_cache;
-  results_lean(g, ra, stg[warp][lane >> 4], valid ? s : 0, valid, lane, !lra_scan);
-  if (lra_scan) {
-    for (int q = 0; q < 2; q++)
-      if (s0 + q < n_streams) results_for_stream<R_LRA | R_GATHER>(g, ra, ra.energies, ra.bounds, s0 + q, lane);
-  }
+  results_lean_pair(g, ra, &stg[warp][0][0], s0 < n_streams ? s0 : 0, s0 < n_streams, s0 + 1 < n_streams, lane);
 }
 
 cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
                            size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches,
-                           uint64_t gate_first, uint64_t gate_last, const GatherArgs* ga, int lra_from_cache, int lean) {
+                           uint64_t gate_first, uint64_t gate_last, const GatherArgs* ga, int lra_from_cache, int lean,
+                           int st_back) {
   if (!st.n_streams) return cudaSuccess;
   const double* ring_e = nullptr;
   if (st.ring && st.ring_e) {
@@ -291,6 +285,8 @@ cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t bu
   if (ga) ra.ga = *ga;
   ra.lra_from_cache = lra_from_cache;
   ra.lean = (lean && !st.ring && g.channels <= kLeanMaxChannels) ? 1 : 0;
+  ra.st_back = ra.lean ? st_back : -1;
+  ra.lra_fast = ra.st_back >= 0 ? 1 : 0;
   if (ra.lean) {
     k_results_lean<<<(unsigned)((st.n_streams + 7) / 8), tpb, 0, s>>>(g, ra, st.n_streams);
   } else {

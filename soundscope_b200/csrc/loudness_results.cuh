@@ -255,6 +255,10 @@ __device__ __forceinline__ void results_for_stream(const GateParams& g, const Re
     }
     pw = warp_sum(pw);
     cnt = warp_sum_u64(cnt);
+    if (lane == 0) {   // the running sums lra_scan_fast continues from
+      ra.cache[s].n_st = cnt;
+      ra.cache[s].sum_st = pw;
+    }
     if (!cnt) lra = 0.0;
     else {
       const double stl_integrated = 0.01 * (pw / (double)cnt);  // 10^(-20/10)
@@ -373,8 +377,14 @@ __device__ __forceinline__ int guess_histogram_index(double loudness) {
 // All 32 lanes call this; lanes 16 g .. 16 g + 15 serve stream s (valid: the group has a stream).  `stg`: this group's
 // kLeanSlots * C doubles of shared memory.  finish_row: write o[3] from the cache and publish the row (false when an
 // LRA scan follows).  Control flow is warp-uniform around every shuffle; loads and stores are predicated on `valid`.
-__device__ __forceinline__ void results_lean(const GateParams& g, const ResultsArgs& ra, double* __restrict__ stg,
-                                             const size_t s, const bool valid, const int lane, const bool finish_row) {
+struct LeanSt {        // what a lean call hands to lra_scan_fast (equal in the 16 lanes of a stream)
+  int st_bin;          // bin of the 3 s entry this call gated (-1: none, or below the absolute gate)
+  unsigned long long n_st;
+  double sum_st;       // StreamCache::n_st / sum_st including that entry
+};
+
+__device__ __forceinline__ LeanSt results_lean(const GateParams& g, const ResultsArgs& ra, double* __restrict__ stg,
+                                               const size_t s, const bool valid, const int lane, const bool finish_row) {
   const int C = g.channels;
   const int gl = lane & 15, gbase = lane & 16;
   const unsigned gmask = 0xffffu << gbase;
@@ -397,7 +407,7 @@ __device__ __forceinline__ void results_lean(const GateParams& g, const ResultsA
     v[t] = (valid && i < nval) ? __ldcg(&bkp[c * kNB + (int)((J - (uint64_t)(kLeanSlots - 1) + (uint64_t)m) % kNB)]) : 0.0;
   }
   unsigned long long cw = 0;
-  if (valid && gl < 6) cw = __ldcg(reinterpret_cast<const unsigned long long*>(&ra.cache[s]) + gl);
+  if (valid && gl < 8) cw = __ldcg(reinterpret_cast<const unsigned long long*>(&ra.cache[s]) + gl);
   float spv = 0.f, tpv = 0.f;
   if (valid && gl < C) {
     spv = __ldcg(&ra.speak[s * C + gl]);
@@ -419,6 +429,10 @@ __device__ __forceinline__ void results_lean(const GateParams& g, const ResultsA
     const uint64_t j = ra.gate_first + (uint64_t)(gl - 2);
     act = pending && j <= ra.gate_last && j >= 3 && g.do_i;
     back = act ? (int)(ra.buckets_done - 1 - j) : 0;
+  } else if (gl == 2 + kLeanPending) {   // the 3 s entry among the pending buckets (lra_fast launches)
+    len = 30;
+    act = ra.lra_fast && ra.st_back >= 0 && g.do_lra;
+    back = act ? ra.st_back : 0;
   }
   double e = 0.0;
   for (int c = 0; c < C; c++) {
@@ -443,10 +457,11 @@ __device__ __forceinline__ void results_lean(const GateParams& g, const ResultsA
   // ---- 3. loudness of my window; block lanes: histogram bin ----
   const double l = energy_to_loudness(e);
   const double lout = act ? (e <= 0.0 ? NEG_INF : l) : NaN;   // lanes 0 / 1: short-term / momentary
-  const bool ok_b = act && gl >= 2 && e >= ra.bound0;
-  int idx = ok_b ? guess_histogram_index(l) : 0;
+  const bool ok_bin = act && gl >= 2 && e >= ra.bound0;   // lanes that enter a histogram: blocks and the 3 s entry
+  const bool ok_b = ok_bin && gl < 2 + kLeanPending;
+  int idx = ok_bin ? guess_histogram_index(l) : 0;
   double en = 0.0;
-  if (ok_b) {
+  if (ok_bin) {
     const double b_lo = __ldg(&ra.bounds[idx]), b_hi = __ldg(&ra.bounds[idx + 1]);
     en = __ldg(&ra.energies[idx]);
     const int fixed = fix_histogram_index(ra.bounds, e, idx, b_lo, b_hi);
@@ -460,6 +475,16 @@ __device__ __forceinline__ void results_lean(const GateParams& g, const ResultsA
   double sum_above = __longlong_as_double((long long)__shfl_sync(0xffffffffu, cw, gbase + 3));
   const int start = (int)(long long)__shfl_sync(0xffffffffu, cw, gbase + 4);
   const double lra_cached = __longlong_as_double((long long)__shfl_sync(0xffffffffu, cw, gbase + 5));
+  LeanSt st;
+  st.n_st = __shfl_sync(0xffffffffu, cw, gbase + 6);
+  st.sum_st = __longlong_as_double((long long)__shfl_sync(0xffffffffu, cw, gbase + 7));
+  {
+    const bool st_ok = __shfl_sync(0xffffffffu, (int)ok_bin, gbase + 2 + kLeanPending) != 0;
+    const int st_idx = __shfl_sync(0xffffffffu, idx, gbase + 2 + kLeanPending);
+    const double st_en = __shfl_sync(0xffffffffu, en, gbase + 2 + kLeanPending);
+    st.st_bin = st_ok ? st_idx : -1;
+    if (st_ok) { st.n_st += 1; st.sum_st += st_en; }
+  }
   n_all += (unsigned long long)__popc(__ballot_sync(0xffffffffu, ok_b) & gmask);
   sum_all += group_sum16(ok_b ? en : 0.0);
   int start_new = start;
@@ -525,14 +550,119 @@ __device__ __forceinline__ void results_lean(const GateParams& g, const ResultsA
       }
     }
   }
-  if (valid && gl < 5) {
+  if (valid && (gl < 5 || ((gl == 6 || gl == 7) && st.st_bin >= 0))) {
     const unsigned long long wv = gl == 0 ? n_all : gl == 1 ? (unsigned long long)__double_as_longlong(sum_all)
                                   : gl == 2 ? n_above : gl == 3 ? (unsigned long long)__double_as_longlong(sum_above)
-                                  : (unsigned long long)(long long)start_new;
+                                  : gl == 4 ? (unsigned long long)(long long)start_new
+                                  : gl == 6 ? st.n_st : (unsigned long long)__double_as_longlong(st.sum_st);
     reinterpret_cast<unsigned long long*>(&ra.cache[s])[gl] = wv;
   }
   __syncwarp();
   if (valid && ok_b) atomicAdd(&ra.block_hist_rw[s * kHistBins + idx], 1u);
+  return st;
+}
+
+// The loudness range of stream s on a launch whose 3 s entry the lean code has gated (ebur128 loudness_range, histogram
+// branch, EBU Tech 3342): one warp per stream.  The first pass over the histogram (count and energy sum of all entries)
+// comes from the cache, so the chain is: histogram loads -> relative gate's bin (one table round trip) -> prefix scan and
+// percentile walk in registers -> the two bin energies (one round trip).  Writes o[3], the cache, and publishes the row.
+__device__ __forceinline__ void lra_scan_fast(const ResultsArgs& ra, const size_t s, const int lane, const int st_bin,
+                                              const unsigned long long n_st, const double sum_st, const size_t stride) {
+  const int bin0 = lane * 32;
+  uint32_t hl_[32];
+  {
+    const uint4* hs4 = reinterpret_cast<const uint4*>(ra.st_hist + s * kHistBins) + lane * 8;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      uint4 w = make_uint4(0, 0, 0, 0);
+      if (bin0 + 4 * q < kHistBins) w = __ldcg(hs4 + q);
+      hl_[4 * q] = w.x; hl_[4 * q + 1] = w.y; hl_[4 * q + 2] = w.z; hl_[4 * q + 3] = w.w;
+    }
+  }
+  double lra = 0.0;
+  if (n_st) {
+    const double stl_integrated = 0.01 * (sum_st / (double)n_st);  // 10^(-20/10)
+    int index = 0;
+    if (!(stl_integrated < ra.bound0)) {
+      index = guess_histogram_index(energy_to_loudness(stl_integrated));
+      const double b_lo = __ldg(&ra.bounds[index]), b_hi = __ldg(&ra.bounds[index + 1]);
+      index = fix_histogram_index(ra.bounds, stl_integrated, index, b_lo, b_hi);
+      if (stl_integrated > __ldg(&ra.energies[index])) ++index;
+    }
+    // the new entry goes into the register copy of its bin (the atomic below is not read back)
+#pragma unroll
+    for (int t = 0; t < 32; t++) hl_[t] += (bin0 + t == st_bin) ? 1u : 0u;
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int t = 0; t < 32; t++) if (bin0 + t >= index) mine += hl_[t];
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+      const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o2);
+      if (lane >= o2) incl += up;
+    }
+    const unsigned long long above = __shfl_sync(0xffffffffu, incl, 31);
+    if (above) {
+      const unsigned long long excl = incl - mine;
+      const unsigned long long lo = (unsigned long long)((double)(above - 1) * 0.1 + 0.5);
+      const unsigned long long hi = (unsigned long long)((double)(above - 1) * 0.95 + 0.5);
+      int lo_bin = -1, hi_bin = -1;
+      unsigned long long run = excl;
+#pragma unroll
+      for (int t = 0; t < 32; t++) {
+        if (bin0 + t >= index) {
+          run += hl_[t];
+          if (lo_bin < 0 && run > lo && excl <= lo) lo_bin = bin0 + t;
+          if (hi_bin < 0 && run > hi && excl <= hi) hi_bin = bin0 + t;
+        }
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        lo_bin = max(lo_bin, __shfl_xor_sync(0xffffffffu, lo_bin, o2));
+        hi_bin = max(hi_bin, __shfl_xor_sync(0xffffffffu, hi_bin, o2));
+      }
+      lra = energy_to_loudness(__ldg(&ra.energies[hi_bin])) - energy_to_loudness(__ldg(&ra.energies[lo_bin]));
+    }
+  }
+  __syncwarp();   // every lane's histogram loads have returned
+  double* o = ra.out + s * stride;
+  if (lane == 0) {
+    if (st_bin >= 0) atomicAdd(&ra.st_hist_rw[s * kHistBins + st_bin], 1u);
+    o[3] = lra;
+    ra.cache[s].lra = lra;
+  }
+  if (ra.ga.world > 0) {
+    __syncwarp();
+    for (size_t i = lane; i < stride; i += 32) {
+      const double v = __ldcg(&o[i]);
+      for (int p = 0; p < ra.ga.world; p++) {
+        double* dst = ra.ga.rows[p] + s * stride + i;
+        if (dst != &o[i]) *dst = v;
+      }
+    }
+  }
+}
+
+// The rows of streams s0 and s0 + 1 (valid0 / valid1) by one warp: the lean pass for both at once, then — on launches
+// that gate a 3 s entry — each stream's loudness range.  `stg`: 2 * kLeanSlots * C doubles of shared memory.
+__device__ __forceinline__ void results_lean_pair(const GateParams& g, const ResultsArgs& ra, double* __restrict__ stg,
+                                                  const size_t s0, const bool valid0, const bool valid1, const int lane) {
+  const bool lra_scan = (ra.mode & SSB_MODE_LRA) == SSB_MODE_LRA && !ra.lra_from_cache;
+  const int grp = lane >> 4;
+  const bool valid = grp ? valid1 : valid0;
+  const LeanSt st = results_lean(g, ra, stg + grp * (kLeanSlots * g.channels), valid ? s0 + grp : s0, valid, lane, !lra_scan);
+  if (lra_scan) {
+    const size_t stride = 4 + 2 * (size_t)g.channels;
+    for (int q = 0; q < 2; q++) {
+      const int st_bin = __shfl_sync(0xffffffffu, st.st_bin, q * 16);
+      const unsigned long long n_st = __shfl_sync(0xffffffffu, st.n_st, q * 16);
+      const double sum_st = __shfl_sync(0xffffffffu, st.sum_st, q * 16);
+      if (q ? valid1 : valid0) {
+        if (ra.lra_fast) lra_scan_fast(ra, s0 + q, lane, st_bin, n_st, sum_st, stride);
+        else results_for_stream<R_LRA | R_GATHER>(g, ra, ra.energies, ra.bounds, s0 + q, lane);
+      }
+    }
+  }
 }
 
 }  // namespace ssb

@@ -639,22 +639,14 @@ k_loudness_wtile(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
       if (n_task) {
         // the bucket sums (P2 warp) and peaks (P1 warp) of the pair's streams are visible to both warps after this
         asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
-        double* stg = reinterpret_cast<double*>(stages) + ((is_p1 ? 2 : 0) + (lane >> 4)) * (kLeanSlots * C);
-        const bool lra_scan = (ra.mode & SSB_MODE_LRA) == SSB_MODE_LRA && !ra.lra_from_cache;
+        double* stg = reinterpret_cast<double*>(stages) + (is_p1 ? 2 : 0) * (kLeanSlots * C);
         for (unsigned task = 0; task < n_task; task++) {
           const unsigned rp = min(rows_per_pass, cta_rows - task * rows_per_pass);
           const unsigned nrows = min(R, rp - gm.warp_off);
           const size_t row_g = (size_t)row0 + task * rows_per_pass + gm.warp_off;
           for (unsigned item = (task + (is_p1 ? 1u : 0u)) & 1u; item * 2 < nrows; item += 2) {
-            const unsigned r = item * 2 + (unsigned)(lane >> 4);
-            const bool valid = r < nrows;
             __syncwarp();   // the previous item's reads of the staging slots are done
-            results_lean(g, ra, stg, row_g + (valid ? r : 0), valid, lane, !lra_scan);
-            if (lra_scan) {
-              for (unsigned q = 0; q < 2; q++)
-                if (item * 2 + q < nrows)
-                  results_for_stream<R_LRA | R_GATHER>(g, ra, ra.energies, ra.bounds, row_g + item * 2 + q, lane);
-            }
+            results_lean_pair(g, ra, stg, row_g + item * 2, true, item * 2 + 1 < nrows, lane);
           }
         }
       }

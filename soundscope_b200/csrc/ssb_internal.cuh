@@ -67,7 +67,8 @@ struct alignas(64) StreamCache {
   double sum_above;
   long long start;
   double lra;
-  double pad[2];
+  unsigned long long n_st;   // short-term (3 s) entries above the absolute gate, and the sum of their bin energies:
+  double sum_st;             // the first pass of ebur128's loudness_range (valid with `lra`)
 };
 
 // --- kernel launchers (loudness.cu) ------------------------------------------------------------
@@ -125,6 +126,9 @@ struct ResultsArgs {
   // lean != 0: the block-histogram sums in `cache` are current and at most kLeanPending buckets are pending, so the
   // integrated loudness is patched instead of re-scanned (results_lean: 16 lanes per stream).
   int lean;
+  // lra_fast != 0 (lean launches that gate a 3 s entry while the cache is current): the lean code gates the entry
+  // (st_back = how many buckets before the last completed one it ends) and lra_scan_fast finishes from the cached sums
+  int lra_fast, st_back;
   double bound0;                   // boundaries[0]: the absolute gate (-70 LUFS) as an energy
 };
 constexpr int kLeanPending = 10;   // pending buckets a lean call can gate (one lane each; at most one 3 s entry among them)
@@ -156,6 +160,8 @@ inline ResultsArgs make_results_args(const LoudState& st, uint64_t buckets_done,
   ra.cache = st.cache;
   ra.lra_from_cache = 0;
   ra.lean = 0;
+  ra.lra_fast = 0;
+  ra.st_back = -1;
   ra.bound0 = histogram_bound0();
   return ra;
 }
@@ -213,7 +219,7 @@ cudaError_t launch_gating(const GateParams& g, const LoudState& st, uint64_t j_f
 cudaError_t launch_results(const GateParams& g, const LoudState& st, uint64_t buckets_done, int aligned,
                            size_t ring_pos, int mode, double* d_out, cudaStream_t s, uint64_t* launches,
                            uint64_t gate_first, uint64_t gate_last, const GatherArgs* ga = nullptr, int lra_from_cache = 0,
-                           int lean = 0);
+                           int lean = 0, int st_back = -1);
 cudaError_t launch_reset(const LoudState& st, int channels, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_histogram_index(const LoudState& st, const double* d_e, size_t n, int32_t* d_out, cudaStream_t s);
 

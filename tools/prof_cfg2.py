@@ -11,7 +11,7 @@ dev = torch.device("cuda", 0)
 an = S.BatchAnalyzer(N_STREAMS, CHANNELS, RATE, mode, device=0)
 an.force_kernel(int(os.environ.get('FORCE', 0)))
 xs = [make_input_device(torch, N_STREAMS, FRAMES, 1234 + i, dev) for i in range(2)]
-for i in range(6):
+for i in range(int(os.environ.get('N_LAUNCH', 6))):
     if os.environ.get('NOFUSE'):
         an.add_frames_device(xs[i & 1])
     else:
