@@ -334,7 +334,14 @@ def timed_e2e_leg(env, an, hx, K, W, launches_per_step, pcm_fmt=None):
     return env.max_over_ranks(time.perf_counter() - t0)
 
 
-def roofline_block(kernel_ms, bytes_per_launch, peak, peak_kind, traffic, kernel_name, filter_only_ms=None):
+BINDING_LOUDNESS = ("FP64 pipe + issue + shared-memory wavefronts all ~60-67 % busy (13 DFMA per sample with the time-segmentation "
+                    "pass), not HBM: DESIGN.md section 3.1")
+BINDING_ALL = ("FMA pipe + issue: the 4x true-peak interpolator is 36 f32 FMA per sample on top of the filter (FFMA 1.5, FFMA2 2.0-2.3 "
+               "cycles per warp instruction measured, profiles/r2_mb_fma.txt), not HBM: DESIGN.md section 3.1")
+
+
+def roofline_block(kernel_ms, bytes_per_launch, peak, peak_kind, traffic, kernel_name, filter_only_ms=None,
+                   binding=BINDING_LOUDNESS):
     """`achieved` / `frac` are for the kernel of the timed region — the fused launch: K-weighting filter + gating + per-stream
     result rows.  `filter_phase_*` is the same kernel launched without that epilogue (what round 1's separate filter kernel
     was), measured right after the timed region on the same inputs."""
@@ -343,7 +350,7 @@ def roofline_block(kernel_ms, bytes_per_launch, peak, peak_kind, traffic, kernel
            "frac": (achieved / peak) if achieved else None, "traffic": traffic,
            "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "kernel_ms": kernel_ms,
            "algorithmic_bytes_per_launch": bytes_per_launch,
-           "binding_resource": "FP64 pipe + issue + shared-memory wavefronts all ~60-67 % busy (13 DFMA per sample with the time-segmentation pass), not HBM: DESIGN.md section 3.1"}
+           "binding_resource": binding}
     if filter_only_ms:
         fo = bytes_per_launch / (filter_only_ms * 1e-3) / 1e9
         out.update({"filter_phase_ms": filter_only_ms, "filter_phase_achieved": fo, "filter_phase_frac": fo / peak})
@@ -445,7 +452,7 @@ def run_ours(args):
         "e2e": e2e["loudness"],
         "gpu_launches": L["launches"],
         "roofline": roofline_block(L["kernel_ms"], samples_per_launch * 4, peak, peak_kind,
-                                   traffic_of("filter_kernel_dram_bytes_per_launch"), "k_loudness_wtile<2,0> (K-weighting + 100 ms energy buckets + gating/results epilogue)",
+                                   traffic_of("filter_kernel_dram_bytes_per_launch"), "k_loudness_wtile<2,0> (K-weighting + 100 ms energy buckets + lean gating/results epilogue)",
                                    L["filter_only_ms"]),
         "cpu_baseline": cpu,
         "ms_per_launch": L["ms_total"] / K / LPS, "launch_overhead_us": (L["ms_total"] / K / LPS - L["kernel_ms"]) * 1e3,
@@ -454,7 +461,7 @@ def run_ours(args):
         "value_all": value_all, "ms_per_step_all": A["ms_total"] / K, "gpu_launches_all": A["launches"],
         "roofline_all": roofline_block(A["kernel_ms"], samples_per_launch * 4, peak, peak_kind,
                                        traffic_of("filter_kernel_all_dram_bytes_per_launch"), "k_loudness_wtile<2,4> (adds sample peak + 4x true-peak FIR, 36 f32 FMA per sample)",
-                                       A["filter_only_ms"]),
+                                       A["filter_only_ms"], BINDING_ALL),
         "e2e_all": e2e["all"], "cpu_baseline_all": cpu_all,
         "e2e_s16": e2e_s16,
         "extras": extras,

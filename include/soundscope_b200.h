@@ -182,6 +182,11 @@ enum { SSB_FFT_MONO = 0, SSB_FFT_MID_SIDE = 1 };
  * SSB_ERR_INVALID_ARG instead of faulting. */
 int32_t ssb_fft_batch_device(ssb_analyzer* h, const float* d_in, int32_t layout, size_t n,
                              size_t n_windows, float* d_db_out, int32_t* d_status);
+/* The same with the reference's y as the output: d_y_out[w][planes][n_bins] f64 = (f64) scale_to_dbfs + tilt, the
+ * addition analyzer.rs:80-94 performs in f64, done in the kernel's store (for SSB_FFT_MONO bit-identical to the y of
+ * ssb_get_fft on the same window).  x comes from ssb_fft_axis.  d_y_out must be 8-byte aligned. */
+int32_t ssb_fft_batch_device_y(ssb_analyzer* h, const float* d_in, int32_t layout, size_t n,
+                               size_t n_windows, double* d_y_out, int32_t* d_status);
 
 /* ---- one player tick in one call (north_star's `Analyzer::process`) ------- */
 /* What tui.rs:1482-1552 (analyze_audio_file_samples) does per playback-position message, fused:

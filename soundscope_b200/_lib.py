@@ -51,7 +51,7 @@ SYMBOLS = [
     "ssb_launch_count", "ssb_add_frames_f32", "ssb_add_frames_f32_device", "ssb_add_frames_f32_device_results", "ssb_add_samples", "ssb_reset",
     "ssb_loudness_momentary", "ssb_loudness_shortterm", "ssb_loudness_global", "ssb_loudness_range",
     "ssb_true_peak", "ssb_sample_peak", "ssb_get_true_peak", "ssb_result_stride", "ssb_results_device",
-    "ssb_calculate_integrated_lufs", "ssb_get_fft", "ssb_fft_bins", "ssb_fft_axis", "ssb_fft_batch_device",
+    "ssb_calculate_integrated_lufs", "ssb_get_fft", "ssb_fft_bins", "ssb_fft_axis", "ssb_fft_batch_device", "ssb_fft_batch_device_y",
     "ssb_process_tick", "ssb_preanalyze_file", "ssb_get_waveform", "ssb_waveform_device", "ssb_mid_side", "ssb_mid_side_device", "ssb_filter_coeffs",
     "ssb_histograms", "ssb_profile_enable", "ssb_profile_read", "ssb_debug_force_generic", "ssb_gather_create", "ssb_gather_open", "ssb_gather_select", "ssb_gather_rows", "ssb_gather_epoch", "ssb_gather_wait", "ssb_gather_destroy",
     "ssb_tick_fft_status", "ssb_true_peak_factor", "ssb_debug_force_true_peak_factor", "ssb_debug_histogram_index",
@@ -121,6 +121,7 @@ def lib():
         "ssb_fft_bins": (C.c_int32, [C.c_size_t, C.c_uint32, szp, szp]),
         "ssb_fft_axis": (C.c_int32, [C.c_size_t, C.c_uint32, f64p, f64p, C.c_size_t, szp]),
         "ssb_fft_batch_device": (C.c_int32, [vp, f32p, C.c_int32, C.c_size_t, C.c_size_t, f32p, vp]),
+        "ssb_fft_batch_device_y": (C.c_int32, [vp, f32p, C.c_int32, C.c_size_t, C.c_size_t, f64p, vp]),
         "ssb_process_tick": (C.c_int32, [vp, f32p, C.c_size_t, C.c_size_t, f64p, f64p, C.c_size_t, szp,
                                          C.POINTER(C.c_double), i32p, i32p]),
         "ssb_preanalyze_file": (C.c_int32, [vp, f32p, C.c_size_t, C.c_uint32, C.c_double, f64p, C.c_size_t, szp,

@@ -240,6 +240,23 @@ class BatchAnalyzer:
                                                   C.c_void_p(out.data_ptr()), sp))
         return out
 
+    def fft_batch_y_device(self, x, out=None, status=None):
+        """Like fft_batch_device, but the kernel writes the reference's y = (f64) dB + tilt (analyzer.rs:80-94):
+        [W, planes, n_bins] f64; pair it with fft_axis(n)[0] for the chart points."""
+        import torch
+        assert x.is_cuda and x.is_contiguous()
+        assert x.data_ptr() % 16 == 0, "fft_batch_y_device: the input view must start on a 16-byte boundary"
+        layout = FFT_MID_SIDE if x.dim() == 3 else FFT_MONO
+        w, n = x.shape[0], x.shape[1]
+        _, nb = self.fft_bins(n)
+        planes = 2 if layout == FFT_MID_SIDE else 1
+        if out is None:
+            out = torch.empty((w, planes, nb), dtype=torch.float64, device=x.device)
+        sp = C.c_void_p(status.data_ptr()) if status is not None else None
+        check(self._h, lib().ssb_fft_batch_device_y(self._h, C.c_void_p(x.data_ptr()), layout, n, w,
+                                                    C.c_void_p(out.data_ptr()), sp))
+        return out
+
     def waveform_device(self, x, waveform_window):
         """x: 1-D f32 CUDA tensor -> [columns, 2] (min, max) f32 CUDA tensor."""
         import torch

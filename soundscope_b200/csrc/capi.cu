@@ -362,6 +362,13 @@ int32_t get_plan(ssb_analyzer* h, size_t n, uint32_t rate, FftPlan** out) {
       CK(cudaMemcpyAsync(p.d_tw_lo, lo.data(), lo.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
       CK(cudaMemcpyAsync(p.d_tw_hi, hi.data(), hi.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
     }
+    {
+      const std::vector<double>& tilt = fft_axis_cached(h, n, rate).second;   // per kept bin, the host's f64 values
+      if (!tilt.empty()) {
+        CK(cudaMalloc(&p.d_tilt, tilt.size() * sizeof(double)));
+        CK(cudaMemcpyAsync(p.d_tilt, tilt.data(), tilt.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      }
+    }
     CK(cudaStreamSynchronize(h->stream));  // w / tw / lo / hi are locals
     it = h->plans.emplace(key, p).first;
   }
@@ -472,6 +479,7 @@ void ssb_analyzer_destroy(ssb_analyzer* h) {
     cudaFree(kv.second.d_twiddle);
     cudaFree(kv.second.d_tw_lo);
     cudaFree(kv.second.d_tw_hi);
+    cudaFree(kv.second.d_tilt);
   }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -811,6 +819,22 @@ int32_t ssb_fft_batch_device(ssb_analyzer* h, const float* d_in, int32_t layout,
   rc = get_plan(h, n, h->rate, &plan);
   if (rc) return rc;
   CK(launch_fft(*plan, d_in, layout, n_windows, d_db_out, d_status, h->stream, &h->launches));
+  return SSB_OK;
+}
+
+int32_t ssb_fft_batch_device_y(ssb_analyzer* h, const float* d_in, int32_t layout, size_t n, size_t n_windows,
+                               double* d_y_out, int32_t* d_status) {
+  if (!h || !d_in || !d_y_out) return SSB_ERR_INVALID_ARG;
+  if (layout != SSB_FFT_MONO && layout != SSB_FFT_MID_SIDE) return fail(h, SSB_ERR_INVALID_ARG, "bad layout");
+  if (((uintptr_t)d_in & 15) != 0 || ((uintptr_t)d_y_out & 7) != 0)
+    return fail(h, SSB_ERR_INVALID_ARG, "ssb_fft_batch_device_y: d_in must be 16-byte aligned (got %p)", (const void*)d_in);
+  int32_t rc = fft_shape_check(n, h->rate);
+  if (rc) return fail(h, rc, "get_fft: invalid length %zu / rate %u", n, h->rate);
+  DeviceGuard g(h->device);
+  FftPlan* plan = nullptr;
+  rc = get_plan(h, n, h->rate, &plan);
+  if (rc) return rc;
+  CK(launch_fft_y(*plan, d_in, layout, n_windows, d_y_out, d_status, h->stream, &h->launches));
   return SSB_OK;
 }
 

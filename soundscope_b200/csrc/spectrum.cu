@@ -99,11 +99,14 @@ __device__ __forceinline__ float mag_to_dbfs_fast(float re, float im, float four
 // LAYOUT 0: mono, in[w][N].  LAYOUT 1: stereo in[w][N][2] -> mid & side planes.
 // LAYOUT 2 / 3: stereo input, only the mid / only the side plane through the packed-real path
 // (used when N complex points do not fit in shared memory).
-template <int LAYOUT>
+// YOUT: the kernel writes the reference's y itself — (f64) dB + tilt[bin], the addition analyzer.rs:80-94 does in f64 —
+// into y_out[w][plane][bin] instead of the f32 dB values (ssb_fft_batch_device_y).
+template <int LAYOUT, bool YOUT = false>
 __global__ void __launch_bounds__(512)
 k_fft(const float* __restrict__ in, unsigned N, const float* __restrict__ window,
       const float2* __restrict__ T, unsigned k_first, unsigned n_bins, float* __restrict__ db_out,
-      unsigned planes_out, unsigned plane_off, int32_t* __restrict__ status) {
+      unsigned planes_out, unsigned plane_off, int32_t* __restrict__ status,
+      const double* __restrict__ tilt = nullptr, double* __restrict__ y_out = nullptr) {
   extern __shared__ float2 z[];
   __shared__ int s_flags[3];  // nan, inf, scaling
   const unsigned w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -158,8 +161,15 @@ k_fft(const float* __restrict__ in, unsigned N, const float* __restrict__ window
       const float2 b = z[dif_position((N - k) & (N - 1), M)];
       const float mr = 0.5f * (a.x + b.x), mi = 0.5f * (a.y - b.y);
       const float sr = 0.5f * (a.y + b.y), si = -0.5f * (a.x - b.x);
-      o_mid[i] = mag_to_dbfs(mr, mi, nf, &bad);
-      o_side[i] = mag_to_dbfs(sr, si, nf, &bad);
+      const float dm = mag_to_dbfs(mr, mi, nf, &bad), ds = mag_to_dbfs(sr, si, nf, &bad);
+      if (YOUT) {
+        const double tl = __ldg(&tilt[i]);
+        y_out[((size_t)w * planes_out + 0) * n_bins + i] = (double)dm + tl;
+        y_out[((size_t)w * planes_out + 1) * n_bins + i] = (double)ds + tl;
+      } else {
+        o_mid[i] = dm;
+        o_side[i] = ds;
+      }
     }
   } else {
     float* o = db_out + ((size_t)w * planes_out + plane_off) * n_bins;
@@ -178,7 +188,9 @@ k_fft(const float* __restrict__ in, unsigned N, const float* __restrict__ window
         xr = sr + (wk.x * di + wk.y * dr);
         xi = si + (wk.y * di - wk.x * dr);
       }
-      o[i] = mag_to_dbfs(xr, xi, nf, &bad);
+      const float dv = mag_to_dbfs(xr, xi, nf, &bad);
+      if (YOUT) y_out[((size_t)w * planes_out + plane_off) * n_bins + i] = (double)dv + __ldg(&tilt[i]);
+      else o[i] = dv;
     }
   }
   if (bad) atomicOr(&s_flags[2], 1);
@@ -217,11 +229,12 @@ __device__ __forceinline__ void run_stage1(float2* z, unsigned M, unsigned N, co
 
 // NT threads per CTA, MINB CTAs per SM: (192, 3) up to M = 8192 (69 KB of shared memory per window),
 // (512, 1) for M = 16384 (135 KB: one window per SM, so the CTA itself has to bring the warps)
-template <int LAYOUT, int NT, int MINB>
+template <int LAYOUT, int NT, int MINB, bool YOUT = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ window,
            const float2* __restrict__ g_lo, const float2* __restrict__ g_hi, unsigned k_first, unsigned n_bins,
-           float* __restrict__ db_out, unsigned planes_out, unsigned plane_off, int32_t* __restrict__ status) {
+           float* __restrict__ db_out, unsigned planes_out, unsigned plane_off, int32_t* __restrict__ status,
+           const double* __restrict__ tilt = nullptr, double* __restrict__ y_out = nullptr) {
   extern __shared__ __align__(16) unsigned char fsm[];
   const unsigned M = (LAYOUT == 1) ? N : (N >> 1);
   const unsigned n_hi = N >> 6;
@@ -341,8 +354,15 @@ k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ w
       const float2 b = z[fft_position((N - k) & (N - 1), r1s)];
       const float mr = 0.5f * (a.x + b.x), mi = 0.5f * (a.y - b.y);
       const float sr = 0.5f * (a.y + b.y), si = -0.5f * (a.x - b.x);
-      o_mid[i] = mag_to_dbfs_fast(mr, mi, four_over_n, &mxo);
-      o_side[i] = mag_to_dbfs_fast(sr, si, four_over_n, &mxo);
+      const float dm = mag_to_dbfs_fast(mr, mi, four_over_n, &mxo), ds = mag_to_dbfs_fast(sr, si, four_over_n, &mxo);
+      if (YOUT) {
+        const double tl = __ldg(&tilt[i]);
+        y_out[((size_t)w * planes_out + 0) * n_bins + i] = (double)dm + tl;
+        y_out[((size_t)w * planes_out + 1) * n_bins + i] = (double)ds + tl;
+      } else {
+        o_mid[i] = dm;
+        o_side[i] = ds;
+      }
     }
   } else {
     float* o = db_out + ((size_t)w * planes_out + plane_off) * n_bins;
@@ -361,7 +381,9 @@ k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ w
         xr = sr + (wk.x * di + wk.y * dr);
         xi = si + (wk.y * di - wk.x * dr);
       }
-      o[i] = mag_to_dbfs_fast(xr, xi, four_over_n, &mxo);
+      const float dv = mag_to_dbfs_fast(xr, xi, four_over_n, &mxo);
+      if (YOUT) y_out[((size_t)w * planes_out + plane_off) * n_bins + i] = (double)dv + __ldg(&tilt[i]);
+      else o[i] = dv;
     }
   }
   if (mxo >= 0x7f800000u) atomicOr(&s_flags[2], 1);
@@ -385,33 +407,33 @@ k_fft_fast(const float* __restrict__ in, unsigned N, const float* __restrict__ w
   }
 }
 
-template <int LAYOUT>
+template <int LAYOUT, bool YOUT = false>
 static cudaError_t launch_fft_layout(const FftPlan& plan, const float* d_in, size_t n_windows, float* d_db,
-                                     unsigned planes_out, unsigned plane_off, int32_t* d_status, cudaStream_t s) {
+                                     unsigned planes_out, unsigned plane_off, int32_t* d_status, cudaStream_t s,
+                                     double* d_y = nullptr) {
   const unsigned N = (unsigned)plan.n;
   const unsigned M = (LAYOUT == 1) ? N : (N >> 1);
   if (M >= 512 && plan.d_tw_lo) {
     const size_t fsmem = (size_t)(64 + (N >> 6)) * sizeof(float2) + 8 + 16 + (size_t)(M + (M >> 5) + (M >> 9) + 1) * sizeof(float2);
     if (M > 8192) {
-      cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+      cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT, 512, 1, YOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
       if (fe) return fe;
-      k_fft_fast<LAYOUT, 512, 1><<<(unsigned)(LAYOUT == 4 ? 2 * n_windows : n_windows), 512, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo, plan.d_tw_hi,
+      k_fft_fast<LAYOUT, 512, 1, YOUT><<<(unsigned)(LAYOUT == 4 ? 2 * n_windows : n_windows), 512, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo, plan.d_tw_hi,
                                                                         (unsigned)plan.k_first, (unsigned)plan.n_bins, d_db,
-                                                                        planes_out, plane_off, d_status);
+                                                                        planes_out, plane_off, d_status, plan.d_tilt, d_y);
     } else {
       // CTA shape for M <= 8192: 256 x 3 (measured 32.5 % of the HBM peak at N = 8192; SSB_FFT_CFG=0 selects
       // 192 x 3: 29.8 %, SSB_FFT_CFG=2 selects 256 x 2: 28.7 %) — a tuning knob, all exact
-      static int cfg = -1;
-      if (cfg < 0) { const char* e = getenv("SSB_FFT_CFG"); cfg = e ? atoi(e) : 1; }
+      static const int cfg = [] { const char* e = getenv("SSB_FFT_CFG"); return e ? atoi(e) : 1; }();   // read once (thread-safe)
 #define SSB_LAUNCH_FFT(NT, MB)                                                                                        \
   do {                                                                                                                 \
-    cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT, NT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+    cudaError_t fe = cudaFuncSetAttribute(k_fft_fast<LAYOUT, NT, MB, YOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)fsmem);                                                                 \
     if (fe) return fe;                                                                                                 \
-    k_fft_fast<LAYOUT, NT, MB><<<(unsigned)(LAYOUT == 4 ? 2 * n_windows : n_windows), NT, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo,            \
+    k_fft_fast<LAYOUT, NT, MB, YOUT><<<(unsigned)(LAYOUT == 4 ? 2 * n_windows : n_windows), NT, fsmem, s>>>(d_in, N, plan.d_window, plan.d_tw_lo,      \
                                                                      plan.d_tw_hi, (unsigned)plan.k_first,             \
                                                                      (unsigned)plan.n_bins, d_db, planes_out,          \
-                                                                     plane_off, d_status);                             \
+                                                                     plane_off, d_status, plan.d_tilt, d_y);           \
   } while (0)
       if (cfg == 0) SSB_LAUNCH_FFT(192, 3);
       else if (cfg == 2) SSB_LAUNCH_FFT(256, 2);
@@ -421,12 +443,12 @@ static cudaError_t launch_fft_layout(const FftPlan& plan, const float* d_in, siz
     return cudaGetLastError();
   }
   const size_t smem = (size_t)(M ? M : 1) * sizeof(float2);
-  cudaError_t e = cudaFuncSetAttribute(k_fft<LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_fft<LAYOUT, YOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e) return e;
   unsigned threads = M / 4 < 64 ? 64 : (M / 4 > 512 ? 512 : M / 4);
-  k_fft<LAYOUT><<<(unsigned)n_windows, threads, smem, s>>>(d_in, N, plan.d_window, plan.d_twiddle,
-                                                          (unsigned)plan.k_first, (unsigned)plan.n_bins, d_db,
-                                                          planes_out, plane_off, d_status);
+  k_fft<LAYOUT, YOUT><<<(unsigned)n_windows, threads, smem, s>>>(d_in, N, plan.d_window, plan.d_twiddle,
+                                                                (unsigned)plan.k_first, (unsigned)plan.n_bins, d_db,
+                                                                planes_out, plane_off, d_status, plan.d_tilt, d_y);
   return cudaGetLastError();
 }
 
@@ -447,6 +469,19 @@ cudaError_t launch_fft(const FftPlan& plan, const float* d_in, int layout, size_
   // N = 16384 / 32768: one N-point complex transform needs 135+ KB of shared memory (one CTA per SM); two packed
   // N/2-point transforms per window (mid, side) in neighbouring CTAs keep three CTAs per SM at N = 16384
   e = launch_fft_layout<4>(plan, d_in, n_windows, d_db_out, 2, 0, d_status, s);
+  if (launches) ++*launches;
+  return e;
+}
+
+// The same transforms with the reference's y = (f64) dB + tilt as the output (d_y_out[w][plane][bin], f64).
+cudaError_t launch_fft_y(const FftPlan& plan, const float* d_in, int layout, size_t n_windows, double* d_y_out,
+                         int32_t* d_status, cudaStream_t s, uint64_t* launches) {
+  if (!n_windows) return cudaSuccess;
+  if (!plan.d_tilt) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (layout == SSB_FFT_MONO) e = launch_fft_layout<0, true>(plan, d_in, n_windows, nullptr, 1, 0, d_status, s, d_y_out);
+  else if (plan.n <= 8192) e = launch_fft_layout<1, true>(plan, d_in, n_windows, nullptr, 2, 0, d_status, s, d_y_out);
+  else e = launch_fft_layout<4, true>(plan, d_in, n_windows, nullptr, 2, 0, d_status, s, d_y_out);
   if (launches) ++*launches;
   return e;
 }

@@ -232,9 +232,12 @@ struct FftPlan {
   float2* d_twiddle = nullptr; // [n/2] exp(-j*2*pi*k/n)
   float2* d_tw_lo = nullptr;   // [64]   W_n^i           (two-level table of the fast kernel)
   float2* d_tw_hi = nullptr;   // [n/64] W_n^(64 i)
+  double* d_tilt = nullptr;    // [n_bins] the f64 tilt of analyzer.rs:80-94 per kept bin (launch_fft_y)
 };
 cudaError_t launch_fft(const FftPlan& plan, const float* d_in, int layout, size_t n_windows,
                        float* d_db_out, int32_t* d_status, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_fft_y(const FftPlan& plan, const float* d_in, int layout, size_t n_windows,
+                         double* d_y_out, int32_t* d_status, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_waveform(const float* d_samples, size_t len, size_t window, float* d_minmax,
                             size_t columns, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_mid_side(const float* d_in, size_t frames, float* d_mid, float* d_side,

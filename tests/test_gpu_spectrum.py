@@ -123,6 +123,32 @@ def test_fft_batch_mid_side(ssb, oracle, cuda, n, rate):
         assert_db_close(dbm[i, 0].astype(np.float64) + tilt, oracle.get_fft(mono[i], rate)[:, 1])
 
 
+@pytest.mark.parametrize("n,rate", [(1024, 44100), (8192, 48000), (16384, 48000), (256, 48000)])
+def test_fft_batch_y_output_is_get_fft_y(ssb, cuda, n, rate):
+    """ssb_fft_batch_device_y: the kernel's store adds the f64 tilt, so the batched result IS get_fft's y
+    (analyzer.rs:67-102): bit-identical to the f32 dB of ssb_fft_batch_device plus the host's tilt (same f64 addition)
+    in every layout, and — mono layout, same kernel — to Analyzer.get_fft of the same window."""
+    torch = cuda
+    w = 6
+    rng = np.random.default_rng(7 * n + rate)
+    x = (0.3 * rng.standard_normal((w, n, 2))).astype(np.float32)
+    b = ssb.BatchAnalyzer(1, 2, rate)
+    xs, tilt = b.fft_axis(n)
+    xd = torch.from_numpy(x).cuda()
+    st = torch.full((w, 2), -1, dtype=torch.int32, device="cuda")
+    y = b.fft_batch_y_device(xd, status=st).cpu().numpy()
+    db = b.fft_batch_device(xd).cpu().numpy()
+    assert y.dtype == np.float64 and y.shape == db.shape and np.all(st.cpu().numpy() == 0)
+    assert np.array_equal(y, db.astype(np.float64) + tilt[None, None, :])
+    mono = torch.from_numpy(np.ascontiguousarray(x[:, :, 0])).cuda()
+    ym = b.fft_batch_y_device(mono).cpu().numpy()
+    a = ssb.Analyzer()
+    a.create_loudness_meter(2, rate)
+    for i in range(w):
+        pts = a.get_fft(x[i, :, 0])
+        assert np.array_equal(pts[:, 0], xs) and np.array_equal(pts[:, 1], ym[i, 0])
+
+
 def test_fft_batch_status_flags(ssb, cuda):
     torch = cuda
     x = np.zeros((3, 1024, 2), dtype=np.float32)
