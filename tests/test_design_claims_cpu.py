@@ -1,5 +1,5 @@
-"""CPU checks of two numerical claims DESIGN.md builds kernels on (no GPU, no product code: scipy's f64 filter and
-the oracle's K-weighting coefficients).
+"""CPU checks of the numerical claims DESIGN.md builds kernels on (no GPU, no product code: scipy's f64 filter, the
+oracle's K-weighting coefficients and histogram tables).
 
 1. File mode (loudness_scan.cu): a chunk of a file that starts 0.4 s early from ZERO filter state reproduces, after the
    run-in, the serial recursion over the whole file down to that recursion's own rounding noise.  The inherited state
@@ -8,6 +8,10 @@ the oracle's K-weighting coefficients).
    time-segmented batch kernel's hand-off sits there too), i.e. < 1e-9 LU on a block energy.
 2. Power-of-two input scaling commutes exactly with the recursion and the energy sums (what lets raw integer PCM run
    through the filter unscaled).
+3. The lean results path (loudness_results.cuh: results_lean): ebur128's two-pass histogram gating
+   can be carried as running sums — totals of every block, the relative gate's start bin, totals of the bins from the
+   start bin up — patched per query with the new blocks and with the bins the gate moved across.  A numpy model of that
+   update rule is run against the two-pass scan of the same histogram after every query.
 """
 import numpy as np
 import pytest
@@ -58,3 +62,86 @@ def test_power_of_two_scaling_commutes_with_the_filter_and_the_energy_sums(oracl
     e_int = np.add.reduceat(y_int * y_int, np.arange(0, q.size, 4800))
     e_flt = np.add.reduceat(y_flt * y_flt, np.arange(0, q.size, 4800))
     assert np.array_equal(e_int / 2.0 ** 30, e_flt)
+
+
+def _tables(oracle):
+    en = np.array([oracle.histogram_energy(i) for i in range(1000)])
+    bd = np.array([oracle.histogram_boundary(i) for i in range(1001)])
+    return en, bd
+
+
+def _two_pass(hist, en, bd, find):
+    """ebur128 gated_loudness, histogram branch (what results_for_stream computes): -> (start bin, LUFS)."""
+    n = int(hist.sum())
+    if n == 0:
+        return 0, -np.inf
+    rel = float((hist * en).sum()) / n
+    rel *= 0.1
+    if rel < bd[0]:
+        start = 0
+    else:
+        start = find(rel)
+        if rel > en[start]:
+            start += 1
+    na = int(hist[start:].sum())
+    if na == 0:
+        return start, -np.inf
+    return start, 10.0 * np.log10(float((hist[start:] * en[start:]).sum()) / na) - 0.691
+
+
+@pytest.mark.parametrize("per_query,seed", [(1, 0), (4, 1), (10, 2), (3, 3)])
+def test_incremental_gating_matches_the_two_pass_histogram_scan(oracle, per_query, seed):
+    en, bd = _tables(oracle)
+    find = oracle.find_histogram_index
+    rng = np.random.default_rng(seed)
+    # block loudness: a slow sweep over 45 LU with jitter, stretches below the absolute gate, abrupt level jumps
+    n_blocks = 3000
+    t = np.arange(n_blocks)
+    lufs = -35.0 + 22.0 * np.sin(2 * np.pi * t / 700.0) + 3.0 * rng.standard_normal(n_blocks)
+    for s0 in rng.integers(0, n_blocks - 40, 12):
+        lufs[s0:s0 + 40] = -90.0
+    lufs[1500:1600] += 30.0
+    energy = 10.0 ** ((lufs + 0.691) / 10.0)
+    hist = np.zeros(1000, dtype=np.int64)
+    # the cache (StreamCache): all zero is the empty meter
+    n_all, sum_all, n_above, sum_above, start = 0, 0.0, 0, 0.0, 0
+    moved = 0
+    for q0 in range(0, n_blocks, per_query):
+        new = [(find(e), e) for e in energy[q0:q0 + per_query] if e >= bd[0]]
+        # --- results_lean's update rule ---
+        n_all += len(new)
+        sum_all += sum(en[b] for b, _ in new)
+        start_new = start
+        if n_all:
+            rel = sum_all / n_all
+            rel *= 0.1
+            if rel < bd[0]:
+                start_new = 0
+            else:
+                start_new = find(rel)
+                if rel > en[start_new]:
+                    start_new += 1
+        lo, hi = min(start, start_new), min(max(start, start_new), 1000)
+        dn, ds = int(hist[lo:hi].sum()), float((hist[lo:hi] * en[lo:hi]).sum())      # the OLD histogram's bins in between
+        if start_new > start:
+            n_above -= dn
+            sum_above -= ds
+        else:
+            n_above += dn
+            sum_above += ds
+        moved += start_new != start
+        for b, _ in new:
+            if b >= start_new:
+                n_above += 1
+                sum_above += en[b]
+        if n_above == 0:
+            sum_above = 0.0
+        start = start_new
+        lean = 10.0 * np.log10(sum_above / n_above) - 0.691 if (n_all and n_above) else -np.inf
+        for b, _ in new:            # the atomics go out last
+            hist[b] += 1
+        # --- against the scan ---
+        want_start, want = _two_pass(hist, en, bd, find)
+        assert start == want_start and n_all == hist.sum() and n_above == hist[start:].sum()
+        assert (np.isneginf(lean) and np.isneginf(want)) or abs(lean - want) <= 1e-9
+    assert moved > 50          # the gate did travel
