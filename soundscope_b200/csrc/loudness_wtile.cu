@@ -5,22 +5,25 @@
 // DF-II K-weighting in f64, y^2 summed per 100 ms, sample peak, polyphase true peak) followed, optionally in the
 // same launch, by the queries of src/analyzer.rs:147-164 (loudness_results.cuh).
 //
-// What bounds it: the FP64 pipe (16 lanes per SM sub-partition: a warp DFMA holds it for 2 cycles), not HBM — a
-// sample costs 9 DFMA (recursion 4, output 4, square 1), and splitting time across lanes adds a zero-state pass
+// What bounds it: the FP64 pipe (16 lanes per SM sub-partition: a warp DFMA holds it for 2 cycles) and the issue port, not
+// HBM — a sample costs 9 DFMA (recursion 4, output 4, square 1), and splitting time across lanes adds a zero-state pass
 // (4 DFMA) and a state hand-off.  So the design rule is "every sub-partition issues the same number of DFMA":
-//   * one persistent CTA per SM, 8 compute warps = 2 per sub-partition, no producer warp: every warp owns its
-//     streams, its own 3-stage shared-memory ring and its own mbarriers and issues its own TMA box loads
-//     (cp.async.bulk.tensor.3d, SWIZZLE_128B).  Warps never wait for each other inside the main loop.
-//   * 4096 stereo streams over 148 SMs is 6.9 streams per sub-partition.  A warp's time per tile is its segment
-//     length L whatever the number of active lanes, so the two warps of a sub-partition are typed: warp A takes 4
-//     streams x 2 channels x T=4 time segments (L = 80 frames of a 320-frame tile), warp B takes 3 streams x 2 x T=5
-//     (L = 64).  7 streams cost 80 + 64 = 144 sample steps per 320 frames instead of the 2 x 80 a uniform T = 4
-//     layout pays (the round-1 kernel: 7 of 8 warps live, 2-2-2-1 over the sub-partitions).
+//   * one persistent CTA of 16 warps per SM, no producer warp.  Streams are grouped into 8 sets; a set owns a 3-stage
+//     shared-memory ring with its own mbarriers and is served by TWO warps specialised by pass (see the banner above
+//     run_p1): the P1 warp runs the zero-state recursion, the hand-off algebra and (Mode::all) the peak detectors, the
+//     P2 warp the full filter and the bucket sums; the P2 warp's lane 0 issues the set's TMA box loads
+//     (cp.async.bulk.tensor.3d, SWIZZLE_128B).  Sets never wait for each other inside the main loop.
+//   * 4096 stereo streams over 148 SMs is 6.9 streams per sub-partition.  A warp's time per tile is its segment length L
+//     whatever the number of active lanes, so a sub-partition's two sets are typed: type A takes 4 streams x 2 channels
+//     x T=4 time segments (L = 80 frames of a 320-frame tile), type B takes 3 streams x 2 x T=5 (L = 64).  7 streams
+//     cost 80 + 64 = 144 sample steps per 320 frames instead of the 2 x 80 a uniform T = 4 layout pays (the round-1
+//     kernel: 7 of 8 warps live, 2-2-2-1 over the sub-partitions).
 //   * per sample the output tap is computed as y / b0 = x + sum (b_i / b0 - a_i) v_i: 4 DFMA instead of 5, the
-//     b0^2 applied once per tile to the partial sum.
-//   * pass 1 of tile t+1 (zero-state recursion, one dependent chain) runs inside the pass-2 loop of tile t.
-//   * after the last tile the CTA's warps gate the completed 100 ms buckets and write the result rows of the
-//     CTA's streams (the code of k_results), so "feed 400 ms, read the meters" is one launch.
+//     b0^2 applied once per tile to the partial sum; both recursions are software-pipelined (partial sums of the next
+//     three samples in registers: one dependent DFMA per sample instead of four).
+//   * after a set's last tile its two warps meet on a named barrier, gate the completed 100 ms buckets and write the
+//     result rows of the set's streams (loudness_results.cuh: the lean path, two streams per warp), so "feed 400 ms,
+//     read the meters" is one launch; with a stale cache the CTA falls back to the full histogram scan.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
